@@ -1,0 +1,87 @@
+"""ctypes binding of libcambrian_b200.so (the C ABI declared in include/cambrian_b200.h).
+
+There is NO fallback: if the shared library is missing or an entry point fails, the caller gets an
+exception.  PyTorch is used only for device memory and streams (tensor.data_ptr(), current stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libcambrian_b200.so"
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_vpp = C.POINTER(C.c_void_p)
+_ip = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes); must list every symbol include/cambrian_b200.h declares
+SIGNATURES = {
+    "cb_version": (_i, []),
+    "cb_last_error": (C.c_char_p, []),
+    "cb_sm_count": (_i, []),
+    "cb_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i, _i,
+                          _vp, _vp, _vp, _i64, _i64, _f, _i, _i, _i, _i, _vp]),
+    "cb_sva_window_attn_fwd": (_i, [_vp, _vp, _vp, _i, _vpp, _vpp, _vpp, _ip, _i, _i, _i, _vp]),
+    "cb_sva_window_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vpp, _vpp, _vpp, _vpp, _vpp, _ip,
+                                    _i, _i, _i, _vp]),
+    "cb_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp, _i, _i, _vp]),
+    "cb_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _vp, _i, _i, _vp]),
+    "cb_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _f, _i, _vp]),
+    "cb_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _vp]),
+    "cb_norm_bwd_workspace_floats": (_i64, [_i64, _i]),
+}
+
+_lib = None
+
+
+class CambrianB200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Fails loudly: the product has no CPU / eager fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise CambrianB200Error(
+            f"{LIB_PATH} not found — build it with `python -m cambrian_b200.build` "
+            "(there is no PyTorch/CPU fallback for the hot path)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    msg = load().cb_last_error().decode(errors="replace")
+    if rc == 1:
+        raise ValueError(f"{what}: {msg}")
+    raise CambrianB200Error(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def int_array(vals):
+    return (C.c_int * len(vals))(*vals)

@@ -1,0 +1,395 @@
+// cambrian_b200 — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[b] (M x N, row-major)  (+)=  epilogue( alpha * A[b] (M x K) * B[b] (K x N) )
+//
+// Every dense contraction on the Cambrian hot path goes through this kernel: ViT / ConvNeXt
+// linear layers, the SVA projections (A5, A7), mm_projector (A8), the
+// LLaMA q/k/v/o/gate/up/down projections and lm_head (A9, A11) and all of their backward
+// GEMMs (dX = dY*W, dW = dY^T*X), which is why both operands can be K-major or MN-major:
+//     a_mn = 0 : A stored [M, K] (K contiguous)       a_mn = 1 : A stored [K, M] (M contiguous)
+//     b_mn = 0 : B stored [N, K] (nn.Linear weight)   b_mn = 1 : B stored [K, N] (N contiguous)
+//
+// Structure (one CTA per SM, 192 threads):
+//     warp 0      TMA producer   : cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx
+//     warp 1      MMA issuer     : one lane issues tcgen05.mma 128 x BN x 16, accumulators in TMEM
+//     warps 2..5  epilogue       : tcgen05.ld TMEM -> regs -> bias / act / scale / residual -> HBM
+// The TMEM accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace cb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B atom
+
+struct GemmEpilogue {
+  void* C;
+  long long ldc, bsc;
+  const bf16* bias;      // [N] or null
+  const bf16* colscale;  // [N] or null (LayerScale)
+  const bf16* residual;  // [M, N] or null
+  long long ldr, bsr;
+  float alpha;
+  int act;         // 0 none, 1 gelu(erf), 2 gelu(tanh), 3 quick_gelu, 4 silu
+  int out_fp32;    // C dtype: 0 bf16, 1 fp32
+  int accumulate;  // C += result
+  int vec_ok;      // 16-byte vector stores are legal
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128 — powers of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case 1: return gelu_erf(v);
+    case 2: return gelu_tanh(v);
+    case 3: return quick_gelu(v);
+    case 4: return silu(v);
+    default: return v;
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  int M, int N, int K, int batch, GemmEpilogue ep) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte aligned bases
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blocks = (M + BM - 1) / BM;
+  const int n_blocks = (N + BN - 1) / BN;
+  const int tiles_per_batch = m_blocks * n_blocks;
+  const int num_tiles = tiles_per_batch * batch;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_batch;
+        const int r = tile - b * tiles_per_batch;
+        const int m0 = (r % m_blocks) * BM;
+        const int n0 = (r / m_blocks) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_3d(sa, &tmA, full_bar(stage), k0, m0, b);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_3d(sa + i * (64 * BK * 2), &tmA, full_bar(stage), m0 + 64 * i, k0, b);
+          }
+          if (!B_MN) {
+            tma_load_3d(sb, &tmB, full_bar(stage), k0, n0, b);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_3d(sb + i * (64 * BK * 2), &tmB, full_bar(stage), n0 + 64 * i, k0, b);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * 2048, 64 * BK * 2, 1024)
+                                        : make_smem_desc_sw128(sa + k * 32, 0, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024)
+                                        : make_smem_desc_sw128(sb + k * 32, 0, 1024);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot is free once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ============================ epilogue ================================
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are owned by this warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch;
+      const int r = tile - b * tiles_per_batch;
+      const int m0 = (r % m_blocks) * BM;
+      const int n0 = (r / m_blocks) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + lane_grp * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
+                             static_cast<uint32_t>(acc * BN);
+      const long long c_off = static_cast<long long>(b) * ep.bsc + static_cast<long long>(row) * ep.ldc;
+      const long long r_off = static_cast<long long>(b) * ep.bsr + static_cast<long long>(row) * ep.ldr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t rr[32];
+        tmem_ld32(taddr + c * 32, rr);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col >= N) break;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[g * 8 + j]) * ep.alpha;
+            const int nvalid = min(8, N - col);
+            if (ep.bias) {
+              for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(ep.bias[col + j]);
+            }
+            if (ep.act) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
+            }
+            if (ep.colscale) {
+              for (int j = 0; j < nvalid; ++j) v[j] *= __bfloat162float(ep.colscale[col + j]);
+            }
+            if (ep.residual) {
+              if (ep.vec_ok) {
+                float t[8];
+                unpack8(*reinterpret_cast<const uint4*>(ep.residual + r_off + col), t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] += t[j];
+              } else {
+                for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(ep.residual[r_off + col + j]);
+              }
+            }
+            if (ep.out_fp32) {
+              float* cp = reinterpret_cast<float*>(ep.C) + c_off + col;
+              if (ep.vec_ok) {
+                float4* c4 = reinterpret_cast<float4*>(cp);
+                if (ep.accumulate) {
+                  const float4 o0 = c4[0], o1 = c4[1];
+                  v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
+                  v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+                }
+                c4[0] = make_float4(v[0], v[1], v[2], v[3]);
+                c4[1] = make_float4(v[4], v[5], v[6], v[7]);
+              } else {
+                for (int j = 0; j < nvalid; ++j) cp[j] = ep.accumulate ? cp[j] + v[j] : v[j];
+              }
+            } else {
+              bf16* cp = reinterpret_cast<bf16*>(ep.C) + c_off + col;
+              if (ep.vec_ok) {
+                if (ep.accumulate) {
+                  float t[8];
+                  unpack8(*reinterpret_cast<const uint4*>(cp), t);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] += t[j];
+                }
+                *reinterpret_cast<uint4*>(cp) = pack8(v);
+              } else {
+                for (int j = 0; j < nvalid; ++j)
+                  cp[j] = __float2bfloat16(ep.accumulate ? __bfloat162float(cp[j]) + v[j] : v[j]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// 3-D bf16 tensor map: dims (inner, rows, batch), box (64, box_rows, 1), SWIZZLE_128B
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
+                      uint64_t ld_elems, uint64_t batch_stride_elems, uint32_t box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return set_error(CB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0)
+    return set_error(CB_ERR_INVALID, "TMA operand base must be 16-byte aligned");
+  if ((ld_elems % 8) != 0 || (batch > 1 && (batch_stride_elems % 8) != 0))
+    return set_error(CB_ERR_INVALID, "TMA operand strides must be multiples of 8 elements (ld=%llu)",
+                     (unsigned long long)ld_elems);
+  cuuint64_t dims[3] = {inner, rows, batch};
+  cuuint64_t bs = (batch > 1) ? batch_stride_elems * 2 : ld_elems * 2 * (rows ? rows : 1);
+  cuuint64_t strides[2] = {ld_elems * 2, bs};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(CB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CB_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int batch,
+                       const GemmEpilogue& ep, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(CB_ERR_CUDA, "gemm smem attr: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * batch;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, batch, ep);
+  CB_CUDA_LAUNCH_CHECK("gemm_bf16_tcgen05");
+  return CB_OK;
+}
+
+template <int BN>
+static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N,
+                          int K, int batch, const GemmEpilogue& ep, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, M, N, K, batch, ep, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, M, N, K, batch, ep, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tmA, tmB, M, N, K, batch, ep, stream);
+  return launch_gemm<BN, true, true>(tmA, tmB, M, N, K, batch, ep, stream);
+}
+
+int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int batch, long long lda,
+              long long ldb, long long ldc, long long bsa, long long bsb, long long bsc, int a_mn, int b_mn,
+              const void* bias, const void* colscale, const void* residual, long long ldr, long long bsr,
+              float alpha, int act, int out_fp32, int accumulate, int force_bn, cudaStream_t stream) {
+  CB_CHECK_ARG(M > 0 && N > 0 && K > 0 && batch > 0, "gemm: empty problem M=%d N=%d K=%d batch=%d", M, N, K,
+               batch);
+  CB_CHECK_ARG(A && B && C, "gemm: null operand");
+  CB_CHECK_ARG(act >= 0 && act <= 4, "gemm: unknown activation %d", act);
+  CUtensorMap tmA, tmB;
+  int rc;
+  int bn = force_bn;
+  if (bn == 0) {
+    const int sms = device_sm_count();
+    const long long mb = (M + BM - 1) / BM;
+    auto tiles = [&](int b_n) { return mb * ((N + b_n - 1) / b_n) * batch; };
+    if (N > 128 && tiles(256) >= (long long)(sms * 7) / 10) bn = 256;
+    else if (N > 64 && tiles(128) >= (long long)(sms * 6) / 10) bn = 128;
+    else if (N > 128 && tiles(64) > 2LL * sms) bn = 128;
+    else bn = 64;
+  }
+  CB_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "gemm: bad BLOCK_N %d", bn);
+  if (!a_mn) rc = make_tmap_bf16_3d(&tmA, A, K, M, batch, lda, bsa, BM);
+  else       rc = make_tmap_bf16_3d(&tmA, A, M, K, batch, lda, bsa, BK);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap_bf16_3d(&tmB, B, K, N, batch, ldb, bsb, bn);
+  else       rc = make_tmap_bf16_3d(&tmB, B, N, K, batch, ldb, bsb, BK);
+  if (rc) return rc;
+  GemmEpilogue ep;
+  ep.C = C; ep.ldc = ldc; ep.bsc = bsc;
+  ep.bias = static_cast<const bf16*>(bias);
+  ep.colscale = static_cast<const bf16*>(colscale);
+  ep.residual = static_cast<const bf16*>(residual);
+  ep.ldr = ldr; ep.bsr = bsr;
+  ep.alpha = alpha; ep.act = act; ep.out_fp32 = out_fp32; ep.accumulate = accumulate;
+  const int cvec = out_fp32 ? 4 : 8;
+  bool vec = (N % 8 == 0) && (ldc % cvec == 0) && (bsc % cvec == 0) &&
+             ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
+  if (residual)
+    vec = vec && (ldr % 8 == 0) && (bsr % 8 == 0) && ((reinterpret_cast<uintptr_t>(residual) & 15u) == 0);
+  ep.vec_ok = vec ? 1 : 0;
+  switch (bn) {
+    case 256: return dispatch_major<256>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
+    case 128: return dispatch_major<128>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
+    default:  return dispatch_major<64>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
+  }
+}
+
+}  // namespace cb
