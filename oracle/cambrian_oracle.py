@@ -1,0 +1,368 @@
+"""TEST INFRASTRUCTURE ONLY — CPU oracle for the Cambrian-1 image->text hot path.
+
+A functional, fp32, plain-torch restatement of what the reference computes on the path SURVEY.md §8a lists
+(A1-A11).  It is the checker for the CUDA path: only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+cpu_baseline / `--impl reference` leg may import it; the product (`cambrian_b200/`) never does.
+
+Every function takes tensors plus a flat state dict that uses the REFERENCE's parameter names (SURVEY.md §8b
+"State-dict keys"), so the same weights can be loaded into the reference modules, this oracle and the CUDA
+modules.  Pinning status (see tests/test_oracle_pin.py, tests/golden/make_golden.py):
+  * SVA layer / sampler, window rearrange, projectors, connector + splice  — pinned against the reference's own
+    modules imported through oracle/ref_shim.py, and against committed golden fixtures generated from them.
+  * CLIP ViT, DINOv2 ViT, LLaMA decoder layer — pinned against the installed `transformers` implementations
+    the reference delegates to (clip_encoder.py:47, dino_encoder.py:81, cambrian_llama.py:23-24).
+  * SigLIP ViT and ConvNeXt-XXL trunks — the reference delegates to timm 0.9.16 via open_clip, which is NOT
+    installed and cannot be fetched: restated from the published timm definitions; PARITY UNPINNED for these
+    two trunks (structure cross-checked against transformers' SiglipVisionModel / ConvNextModel only).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+IGNORE_INDEX = -100
+IMAGE_TOKEN_INDEX = -200
+
+
+# ------------------------------------------------------------------------------------------------
+# small building blocks
+# ------------------------------------------------------------------------------------------------
+def _lin(sd, name, x, bias=True):
+    b = sd.get(name + ".bias") if bias else None
+    return F.linear(x, sd[name + ".weight"], b)
+
+
+def _ln(sd, name, x, eps=1e-5):
+    return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd.get(name + ".bias"), eps)
+
+
+def quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+def rms_norm(x, w, eps):
+    """train_fsdp.py:1429-1435 (training-time patch): fp32 normalise, multiply by weight, then cast."""
+    xf = x.float()
+    return (w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps))).to(x.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# A6/A7 — Spatial Vision Aggregator
+# ------------------------------------------------------------------------------------------------
+def window_rearrange(feat, q_side):
+    """cambrian_arch.py:271-287: [B, (q r)^2, C] -> [B q^2, r^2, C]."""
+    B, n, C = feat.shape
+    side = int(round(n ** 0.5))
+    assert (side // q_side) * q_side == side
+    r = side // q_side
+    t = feat.view(B, q_side, r, q_side, r, C).permute(0, 1, 3, 2, 4, 5)
+    return t.reshape(B * q_side * q_side, r * r, C)
+
+
+def sva_layer(sd, p, queries, ctx, feats, masks, heads=16):
+    """VisionCrossAttentionLayer.forward, vision_sampler.py:270-327 (+ MultiKVCrossAttention :177-234).
+
+    queries [N,1,Dq]; ctx [N,1,Dc]; feats[i] [N, r_i^2, Dkv]; masks[i] [N, r_i^2] bool (or None)."""
+    n = queries.shape[0]
+    residual = queries
+    c = F.linear(ctx, sd[p + "proj_context.weight"])                        # :279
+    q = F.linear(torch.cat([queries, c], -1), sd[p + "proj_in.weight"])     # :281,:292
+    ks, vs, ms = [], [], []
+    for i, f in enumerate(feats):
+        if f.shape[1] > 1:                                                  # :304-309
+            f = f + sd[p + f"pos_embed_{i}"][None].to(f.dtype)
+        ks.append(_lin(sd, p + f"cross_attn.k_proj_{i}.1", _ln(sd, p + f"cross_attn.k_proj_{i}.0", f), bias=False))
+        vs.append(_lin(sd, p + f"cross_attn.v_proj_{i}.1", _ln(sd, p + f"cross_attn.v_proj_{i}.0", f), bias=False))
+        m = masks[i] if masks is not None and masks[i] is not None else None
+        ms.append(torch.ones(n, f.shape[1], dtype=torch.bool) if m is None else m.view(n, -1).bool())
+    hidden = q.shape[-1]
+    hd = hidden // heads
+    Q = _lin(sd, p + "cross_attn.q_proj.1", _ln(sd, p + "cross_attn.q_proj.0", q), bias=False)
+    Q = Q.view(n, 1, heads, hd).transpose(1, 2)
+    K = torch.cat(ks, 1).view(n, -1, heads, hd).transpose(1, 2)
+    V = torch.cat(vs, 1).view(n, -1, heads, hd).transpose(1, 2)
+    mask = torch.cat(ms, -1)[:, None, None, :]                              # :200
+    s = (Q @ K.transpose(-1, -2)) / math.sqrt(hd)
+    s = s.masked_fill(~mask, float("-inf"))
+    a = (torch.softmax(s, -1) @ V).transpose(1, 2).reshape(n, 1, hidden)    # :215-230
+    a = F.linear(a, sd[p + "cross_attn.o_proj.weight"])                     # :232
+    q = _ln(sd, p + "norm", q + a)                                          # :319-321
+    q = F.linear(F.gelu(F.linear(q, sd[p + "proj_out.linear_1.weight"])), sd[p + "proj_out.linear_2.weight"])
+    return q + residual                                                     # :325
+
+
+def sva_sampler(sd, p, queries, ctx, feats, masks, num_layers):
+    """VisionTokenSampler.forward, vision_sampler.py:416-419."""
+    for l in range(num_layers):
+        queries = sva_layer(sd, f"{p}layers.{l}.", queries, ctx, feats, masks)
+    return queries
+
+
+# ------------------------------------------------------------------------------------------------
+# A5/A8 — projectors, connector, splice (static-shape branch, cambrian_arch.py:366-490)
+# ------------------------------------------------------------------------------------------------
+def mm_projector_aux(sd, p, x):
+    """nn.Sequential(Linear, GELU, Linear, LayerNorm)  cambrian_arch.py:56."""
+    return _ln(sd, p + "3", _lin(sd, p + "2", F.gelu(_lin(sd, p + "0", x))))
+
+
+def mlp2x_gelu(sd, p, x):
+    """nn.Sequential(Linear, GELU, Linear): cambrian_arch.py:49 / multimodal_projector/builder.py:60-67."""
+    return _lin(sd, p + "2", F.gelu(_lin(sd, p + "0", x)))
+
+
+def connector(sd, cfg, tower_feats, aux_masks):
+    """cambrian_arch.py:366-420 (mm_projector_type == 'sva', one query group, static branch).
+
+    tower_feats[i] [B, N_i, C_i]; aux_masks[i] [B*q^2, r_i^2] bool.  Returns image_features [B, q*(q+1), H],
+    rearranged aux features / ctx for the in-LLM SVA layers."""
+    B = tower_feats[0].shape[0]
+    q_num = cfg["image_token_len"]
+    q_side = int(q_num ** 0.5)
+    aux = [mm_projector_aux(sd, f"model.mm_projector_aux_{i}.", f) for i, f in enumerate(tower_feats)]
+    ctx = aux[0].mean(1).view(B, 1, 1, -1)                                   # :377
+    feats_w = [window_rearrange(a, q_side) for a in aux]
+    queries = sd["model.vision_query"][0].view(1, 1, 1, -1).expand(B, q_num, -1, -1).flatten(0, 1)
+    ctx_q = ctx.expand(-1, q_num, 1, -1).flatten(0, 1)
+    qf = sva_sampler(sd, "model.vision_sampler_0.", queries, ctx_q, feats_w, aux_masks, cfg["connector_depth"])
+    img = mlp2x_gelu(sd, "model.mm_projector.", qf.view(B, q_num, -1))       # :410-411
+    img = img.view(B, q_side, q_side, -1)
+    nl = sd["model.image_newline"][None, None, None, :].expand(B, q_side, 1, -1)
+    img = torch.cat([img, nl], 2).flatten(1, 2)                              # :413-420
+    return img, feats_w, ctx_q
+
+
+def splice(sd, input_ids, image_features):
+    """cambrian_arch.py:457-490 static branch, one image per sample: the <image> indicator and the 599 pad ids
+    that follow it are replaced by the 600 image embeddings."""
+    ids = torch.where(input_ids == IMAGE_TOKEN_INDEX, 0, input_ids)
+    emb = F.embedding(ids, sd["model.embed_tokens.weight"]).clone()
+    for b in range(input_ids.shape[0]):
+        pos = torch.where(input_ids[b] == IMAGE_TOKEN_INDEX)[0]
+        if len(pos) == 0:
+            continue
+        s = int(pos[0])
+        L = image_features.shape[1]
+        emb[b, s:s + L] = image_features[b].to(emb.dtype)
+    return emb
+
+
+# ------------------------------------------------------------------------------------------------
+# A9-A11 — LLaMA decoder with SVA insertion, lm_head, loss
+# ------------------------------------------------------------------------------------------------
+def rope_cos_sin(position_ids, head_dim, theta):
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    fr = position_ids[..., None].float() * inv                               # [B,S,hd/2]
+    emb = torch.cat([fr, fr], -1)
+    return emb.cos(), emb.sin()
+
+
+def apply_rope(x, cos, sin):
+    """x [B,h,S,hd]; HF rotate_half convention."""
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return x * cos[:, None] + torch.cat([-x2, x1], -1) * sin[:, None]
+
+
+def llama_layer(sd, p, x, cos, sin, attn_mask_2d, cfg):
+    """HF LlamaDecoderLayer (transformers, called from cambrian_llama.py:142-166)."""
+    B, S, H = x.shape
+    nh, nkv = cfg["num_attention_heads"], cfg["num_key_value_heads"]
+    hd = H // nh
+    h = rms_norm(x, sd[p + "input_layernorm.weight"], cfg["rms_norm_eps"])
+    q = F.linear(h, sd[p + "self_attn.q_proj.weight"]).view(B, S, nh, hd).transpose(1, 2)
+    k = F.linear(h, sd[p + "self_attn.k_proj.weight"]).view(B, S, nkv, hd).transpose(1, 2)
+    v = F.linear(h, sd[p + "self_attn.v_proj.weight"]).view(B, S, nkv, hd).transpose(1, 2)
+    q, k = apply_rope(q, cos, sin), apply_rope(k, cos, sin)
+    k = k.repeat_interleave(nh // nkv, 1)
+    v = v.repeat_interleave(nh // nkv, 1)
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    causal = torch.ones(S, S, dtype=torch.bool).tril()
+    allow = causal[None, None]
+    if attn_mask_2d is not None:
+        allow = allow & attn_mask_2d.bool()[:, None, None, :]
+    s = s.masked_fill(~allow, torch.finfo(s.dtype).min)                      # HF additive-min mask semantics
+    a = (torch.softmax(s.float(), -1).to(s.dtype) @ v).transpose(1, 2).reshape(B, S, H)
+    x = x + F.linear(a, sd[p + "self_attn.o_proj.weight"])
+    h = rms_norm(x, sd[p + "post_attention_layernorm.weight"], cfg["rms_norm_eps"])
+    g = F.silu(F.linear(h, sd[p + "mlp.gate_proj.weight"])) * F.linear(h, sd[p + "mlp.up_proj.weight"])
+    return x + F.linear(g, sd[p + "mlp.down_proj.weight"])
+
+
+def decoder(sd, cfg, inputs_embeds, position_ids, attn_mask_2d, feats_w=None, aux_masks=None, ctx_q=None):
+    """CambrianLlamaModel.forward, cambrian_llama.py:98-277, static SVA-insertion branch :168-207."""
+    x = inputs_embeds
+    B = x.shape[0]
+    hd = cfg["hidden_size"] // cfg["num_attention_heads"]
+    cos, sin = rope_cos_sin(position_ids, hd, cfg["rope_theta"])
+    n_sva = 0 if cfg.get("connector_only", True) else cfg["num_of_vision_sampler_layers"]
+    sites = [cfg["start_of_vision_sampler_layers"] + i * cfg["stride_of_vision_sampler_layers"]
+             for i in range(n_sva)]
+    q_num = cfg.get("image_token_len", 576)
+    side = int(q_num ** 0.5)
+    for i in range(cfg["num_hidden_layers"]):
+        x = llama_layer(sd, f"model.layers.{i}.", x, cos, sin, attn_mask_2d, cfg)
+        if feats_w is not None and i in sites:
+            s0 = cfg["image_position"]
+            blk = x[:, s0:s0 + q_num + side].clone().view(B, side, side + 1, -1)
+            lq, nl = blk[:, :, :-1], blk[:, :, -1:]
+            lq = lq.reshape(B * q_num, 1, -1)
+            lq = sva_sampler(sd, f"model.vision_sampler_layers.{sites.index(i)}.", lq, ctx_q,
+                             [f.to(lq.dtype) for f in feats_w], aux_masks, 1)
+            blk = torch.cat([lq.view(B, side, side, -1), nl], 2).flatten(1, 2)
+            x = x.clone()
+            x[:, s0:s0 + q_num + side] = blk
+    return rms_norm(x, sd["model.norm.weight"], cfg["rms_norm_eps"])
+
+
+def lm_loss(sd, hidden, labels):
+    """cambrian_llama.py:402-422: lm_head -> fp32 logits -> shifted CE (ignore_index -100, mean)."""
+    logits = F.linear(hidden, sd["lm_head.weight"]).float()
+    loss = None
+    if labels is not None:
+        loss = F.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), labels[:, 1:].reshape(-1),
+                               ignore_index=IGNORE_INDEX)
+    return logits, loss
+
+
+# ------------------------------------------------------------------------------------------------
+# A1-A4 — vision towers
+# ------------------------------------------------------------------------------------------------
+def _mha(x, wq, bq, wk, bk, wv, bv, wo, bo, heads):
+    B, S, D = x.shape
+    hd = D // heads
+    q = F.linear(x, wq, bq).view(B, S, heads, hd).transpose(1, 2)
+    k = F.linear(x, wk, bk).view(B, S, heads, hd).transpose(1, 2)
+    v = F.linear(x, wv, bv).view(B, S, heads, hd).transpose(1, 2)
+    a = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), -1) @ v
+    return F.linear(a.transpose(1, 2).reshape(B, S, D), wo, bo)
+
+
+def bilinear_tokens(feat, target_tokens):
+    """clip_encoder.py:70-96 / siglip_encoder.py:67-93 / dino_encoder.py:128-154: fp32 bilinear resize of the
+    token grid (align_corners=False)."""
+    B, n, C = feat.shape
+    if n == target_tokens:
+        return feat
+    h, t = int(n ** 0.5), int(target_tokens ** 0.5)
+    g = feat.view(B, h, h, C).permute(0, 3, 1, 2).float()
+    g = F.interpolate(g, size=(t, t), mode="bilinear", align_corners=False).to(feat.dtype)
+    return g.permute(0, 2, 3, 1).flatten(1, 2)
+
+
+def clip_vit(sd, cfg, images, p="vision_model."):
+    """ClipVisionTower._forward, clip_encoder.py:98-107 -> HF CLIPVisionModel, hidden_states[select_layer]
+    (default -2), CLS dropped (clip_encoder.py:55-68)."""
+    L = cfg["num_hidden_layers"]
+    sel = cfg.get("select_layer", -2)
+    n_run = L + 1 + sel if sel < 0 else sel           # hidden_states has L+1 entries; index -2 => L-1 layers
+    x = F.conv2d(images, sd[p + "embeddings.patch_embedding.weight"], stride=cfg["patch_size"])
+    x = x.flatten(2).transpose(1, 2)
+    cls = sd[p + "embeddings.class_embedding"].expand(x.shape[0], 1, -1)
+    x = torch.cat([cls, x], 1) + sd[p + "embeddings.position_embedding.weight"][None]
+    x = _ln(sd, p + "pre_layrnorm", x)
+    for i in range(n_run):
+        q = f"{p}encoder.layers.{i}."
+        h = _ln(sd, q + "layer_norm1", x)
+        x = x + _mha(h, sd[q + "self_attn.q_proj.weight"], sd[q + "self_attn.q_proj.bias"],
+                     sd[q + "self_attn.k_proj.weight"], sd[q + "self_attn.k_proj.bias"],
+                     sd[q + "self_attn.v_proj.weight"], sd[q + "self_attn.v_proj.bias"],
+                     sd[q + "self_attn.out_proj.weight"], sd[q + "self_attn.out_proj.bias"],
+                     cfg["num_attention_heads"])
+        h = _ln(sd, q + "layer_norm2", x)
+        x = x + _lin(sd, q + "mlp.fc2", quick_gelu(_lin(sd, q + "mlp.fc1", h)))
+    return bilinear_tokens(x[:, 1:], cfg.get("interp", x.shape[1] - 1))
+
+
+def dinov2_pos_embed(pos, grid):
+    """HF Dinov2Embeddings.interpolate_pos_encoding (installed transformers): bicubic, size-based."""
+    n = pos.shape[1] - 1
+    s = int(n ** 0.5)
+    if s == grid:
+        return pos
+    pp = pos[:, 1:].reshape(1, s, s, -1).permute(0, 3, 1, 2).float()
+    pp = F.interpolate(pp, size=(grid, grid), mode="bicubic", align_corners=False).to(pos.dtype)
+    return torch.cat([pos[:, :1], pp.permute(0, 2, 3, 1).reshape(1, grid * grid, -1)], 1)
+
+
+def dinov2_vit(sd, cfg, images):
+    """DinoVisionTower._forward, dino_encoder.py:156-165 -> HF Dinov2Model.last_hidden_state[:, 1:]."""
+    ps = cfg["patch_size"]
+    x = F.conv2d(images, sd["embeddings.patch_embeddings.projection.weight"],
+                 sd["embeddings.patch_embeddings.projection.bias"], stride=ps)
+    grid = x.shape[-1]
+    x = x.flatten(2).transpose(1, 2)
+    x = torch.cat([sd["embeddings.cls_token"].expand(x.shape[0], -1, -1), x], 1)
+    x = x + dinov2_pos_embed(sd["embeddings.position_embeddings"], grid)
+    eps = cfg.get("layer_norm_eps", 1e-6)
+    for i in range(cfg["num_hidden_layers"]):
+        q = f"encoder.layer.{i}."
+        h = _ln(sd, q + "norm1", x, eps)
+        a = _mha(h, sd[q + "attention.attention.query.weight"], sd[q + "attention.attention.query.bias"],
+                 sd[q + "attention.attention.key.weight"], sd[q + "attention.attention.key.bias"],
+                 sd[q + "attention.attention.value.weight"], sd[q + "attention.attention.value.bias"],
+                 sd[q + "attention.output.dense.weight"], sd[q + "attention.output.dense.bias"],
+                 cfg["num_attention_heads"])
+        x = x + a * sd[q + "layer_scale1.lambda1"]
+        h = _ln(sd, q + "norm2", x, eps)
+        m = _lin(sd, q + "mlp.fc2", F.gelu(_lin(sd, q + "mlp.fc1", h)))
+        x = x + m * sd[q + "layer_scale2.lambda1"]
+    x = _ln(sd, "layernorm", x, eps)
+    return bilinear_tokens(x[:, 1:], cfg.get("interp", x.shape[1] - 1))
+
+
+def siglip_vit(sd, cfg, images):
+    """SiglipVisionTower._forward, siglip_encoder.py:95-99 -> timm VisionTransformer.forward_features of
+    vit_so400m_patch14_siglip_384 (class_token=False, learned pos, fused qkv with bias, erf-GELU, final norm,
+    LN eps 1e-6).  timm parameter names.  PARITY UNPINNED (timm not installed)."""
+    x = F.conv2d(images, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=cfg["patch_size"])
+    x = x.flatten(2).transpose(1, 2) + sd["pos_embed"]
+    heads = cfg["num_attention_heads"]
+    act = F.gelu if cfg.get("act", "gelu") == "gelu" else (lambda t: F.gelu(t, approximate="tanh"))
+    for i in range(cfg["num_hidden_layers"]):
+        q = f"blocks.{i}."
+        h = _ln(sd, q + "norm1", x, 1e-6)
+        wq, wk, wv = sd[q + "attn.qkv.weight"].chunk(3, 0)
+        bq, bk, bv = sd[q + "attn.qkv.bias"].chunk(3, 0)
+        x = x + _mha(h, wq, bq, wk, bk, wv, bv, sd[q + "attn.proj.weight"], sd[q + "attn.proj.bias"], heads)
+        h = _ln(sd, q + "norm2", x, 1e-6)
+        x = x + _lin(sd, q + "mlp.fc2", act(_lin(sd, q + "mlp.fc1", h)))
+    x = _ln(sd, "norm", x, 1e-6)
+    return bilinear_tokens(x, cfg.get("interp", x.shape[1]))
+
+
+def _ln2d(sd, name, x, eps=1e-6):
+    return _ln(sd, name, x.permute(0, 2, 3, 1), eps).permute(0, 3, 1, 2)
+
+
+def convnext_trunk(sd, cfg, images):
+    """CLIPConvNextTower._forward, clip_convnext_encoder.py:121-144 -> timm ConvNeXt stem + stages
+    (convnext_xxlarge: depths 3-4-30-3, dims 384-768-1536-3072; block = dwconv7x7 -> LN -> fc1 -> GELU -> fc2
+    -> gamma -> +residual; downsample = LN2d + conv2x2/2).  Returns the last stage (or all 4, multi-stage)
+    bilinearly resized to the interp grid (:99-119) as [B, N, C].  PARITY UNPINNED (timm not installed)."""
+    x = F.conv2d(images, sd["stem.0.weight"], sd["stem.0.bias"], stride=4)
+    x = _ln2d(sd, "stem.1", x)
+    outs = []
+    for s, depth in enumerate(cfg["depths"]):
+        p = f"stages.{s}."
+        if s > 0:
+            x = _ln2d(sd, p + "downsample.0", x)
+            x = F.conv2d(x, sd[p + "downsample.1.weight"], sd[p + "downsample.1.bias"], stride=2)
+        for b in range(depth):
+            q = f"{p}blocks.{b}."
+            h = F.conv2d(x, sd[q + "conv_dw.weight"], sd[q + "conv_dw.bias"], padding=3, groups=x.shape[1])
+            h = h.permute(0, 2, 3, 1)
+            h = _ln(sd, q + "norm", h, 1e-6)
+            h = _lin(sd, q + "mlp.fc2", F.gelu(_lin(sd, q + "mlp.fc1", h)))
+            if (q + "gamma") in sd:
+                h = h * sd[q + "gamma"]
+            x = x + h.permute(0, 3, 1, 2)
+        outs.append(x)
+    feats = outs if cfg.get("multi_stage", False) else outs[-1:]
+    t = int(cfg["interp"] ** 0.5)
+    res = []
+    for f in feats:
+        g = F.interpolate(f.float(), size=(t, t), mode="bilinear", align_corners=False).to(f.dtype)
+        res.append(g.flatten(2).transpose(1, 2))
+    return torch.cat(res, -1)
