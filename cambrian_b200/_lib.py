@@ -32,6 +32,27 @@ SIGNATURES = {
     "cb_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _f, _i, _vp]),
     "cb_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _vp]),
     "cb_norm_bwd_workspace_floats": (_i64, [_i64, _i]),
+    "cb_attn_fwd": (_i, [_vp] * 6 + [_i] * 6 + [_i64] * 8 + [_f, _i, _vp]),
+    "cb_attn_bwd": (_i, [_vp] * 11 + [_i] * 6 + [_i64] * 14 + [_f, _i, _vp]),
+    "cb_act_fwd": (_i, [_vp, _vp, _i64, _i, _vp]),
+    "cb_act_bwd": (_i, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "cb_swiglu_fwd": (_i, [_vp, _vp, _vp, _i64, _i, _i64, _i64, _vp]),
+    "cb_swiglu_bwd": (_i, [_vp] * 5 + [_i64, _i, _i64, _i64, _i64, _vp]),
+    "cb_rope": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i64, _i, _i, _vp]),
+    "cb_embed_splice": (_i, [_vp] * 6 + [_i, _i, _i, _i, _i64, _vp]),
+    "cb_embed_splice_bwd": (_i, [_vp] * 6 + [_i, _i, _i, _i, _i64, _vp]),
+    "cb_add_pos_tokens": (_i, [_vp] * 4 + [_i, _i, _i, _vp]),
+    "cb_bilinear": (_i, [_vp, _vp] + [_i] * 6 + [_i64, _i64, _i, _i, _vp]),
+    "cb_patchify_nchw": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),
+    "cb_patchify_nhwc": (_i, [_vp, _vp] + [_i] * 5 + [_vp]),
+    "cb_dwconv7": (_i, [_vp] * 4 + [_i] * 4 + [_vp]),
+    "cb_add_inplace": (_i, [_vp, _vp, _i64, _vp]),
+    "cb_group_colsum": (_i, [_vp, _vp, _vp, _i, _i64, _i, _f, _i, _vp]),
+    "cb_group_broadcast": (_i, [_vp, _vp, _i, _i64, _i, _f, _i, _vp]),
+    "cb_pos_grad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "cb_f32_to_bf16": (_i, [_vp, _vp, _i64, _i, _i64, _f, _vp]),
+    "cb_cross_entropy": (_i, [_vp] * 4 + [_i64, _i64, _i64, _f, _i, _i64, _vp]),
+    "cb_adamw": (_i, [_vp] * 5 + [_i64] + [_f] * 5 + [_i, _f, _vp]),
 }
 
 _lib = None

@@ -46,6 +46,39 @@ int rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, void
                 long long, int, cudaStream_t);
 long long norm_bwd_workspace_floats(long long, int);
 
+int attn_fwd_launch(const void*, const void*, const void*, void*, float*, const void*, int, int, int, int, int, int,
+                    long long, long long, long long, long long, long long, long long, long long, long long, float, int,
+                    cudaStream_t);
+int attn_bwd_launch(const void*, const void*, const void*, const void*, const void*, const float*, float*, float*, void*,
+                    void*, const void*, int, int, int, int, int, int, long long, long long, long long, long long,
+                    long long, long long, long long, long long, long long, long long, long long, long long, long long,
+                    long long, float, int, cudaStream_t);
+int act_fwd_launch(const void*, void*, long long, int, cudaStream_t);
+int act_bwd_launch(const void*, const void*, void*, long long, int, cudaStream_t);
+int swiglu_fwd_launch(const void*, const void*, void*, long long, int, long long, long long, cudaStream_t);
+int swiglu_bwd_launch(const void*, const void*, const void*, void*, void*, long long, int, long long, long long,
+                      long long, cudaStream_t);
+int rope_launch(void*, const long long*, const float*, const float*, long long, int, int, long long, int, int,
+                cudaStream_t);
+int embed_splice_launch(const long long*, const int*, const void*, const void*, const void*, void*, int, int, int, int,
+                        long long, cudaStream_t);
+int embed_splice_bwd_launch(const void*, const long long*, const int*, void*, void*, void*, int, int, int, int,
+                            long long, cudaStream_t);
+int add_pos_tokens_launch(const void*, const void*, const void*, void*, int, int, int, cudaStream_t);
+int bilinear_launch(const void*, void*, int, int, int, int, int, int, long long, long long, int, int, cudaStream_t);
+int patchify_nchw_launch(const void*, void*, int, int, int, int, int, cudaStream_t);
+int patchify_nhwc_launch(const void*, void*, int, int, int, int, int, cudaStream_t);
+int dwconv7_launch(const void*, const void*, const void*, void*, int, int, int, int, cudaStream_t);
+int add_inplace_launch(void*, const void*, long long, cudaStream_t);
+int group_colsum_launch(const void*, void*, float*, int, long long, int, float, int, cudaStream_t);
+int group_broadcast_launch(const void*, void*, int, long long, int, float, int, cudaStream_t);
+int pos_grad_launch(const void*, void*, int, int, int, int, int, cudaStream_t);
+int f32_to_bf16_launch(const float*, void*, long long, int, long long, float, cudaStream_t);
+int cross_entropy_launch(void*, const long long*, float*, float*, long long, long long, long long, float, int,
+                         long long, cudaStream_t);
+int adamw_launch(float*, float*, float*, const void*, void*, long long, float, float, float, float, float, int, float,
+                 cudaStream_t);
+
 }  // namespace cb
 
 #define ST(s) static_cast<cudaStream_t>(s)
@@ -98,5 +131,93 @@ int cb_rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float
   return cb::rmsnorm_bwd(dy, x, gamma, rstd, dx, dgamma, workspace, workspace_floats, rows, C, ST(stream));
 }
 int64_t cb_norm_bwd_workspace_floats(int64_t rows, int C) { return cb::norm_bwd_workspace_floats(rows, C); }
+
+int cb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const void* kmask, int B, int nh,
+                int nkv, int Sq, int Skv, int hd, int64_t q_bs, int64_t q_ss, int64_t k_bs, int64_t k_ss,
+                int64_t v_bs, int64_t v_ss, int64_t o_bs, int64_t o_ss, float scale, int causal, void* stream) {
+  return cb::attn_fwd_launch(q, k, v, o, lse, kmask, B, nh, nkv, Sq, Skv, hd, q_bs, q_ss, k_bs, k_ss, v_bs, v_ss, o_bs,
+                             o_ss, scale, causal, ST(stream));
+}
+int cb_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                float* delta, float* dq_acc, void* dk, void* dv, const void* kmask, int B, int nh, int nkv, int Sq,
+                int Skv, int hd, int64_t q_bs, int64_t q_ss, int64_t k_bs, int64_t k_ss, int64_t v_bs, int64_t v_ss,
+                int64_t o_bs, int64_t o_ss, int64_t do_bs, int64_t do_ss, int64_t dk_bs, int64_t dk_ss,
+                int64_t dv_bs, int64_t dv_ss, float scale, int causal, void* stream) {
+  return cb::attn_bwd_launch(q, k, v, o, d_o, lse, delta, dq_acc, dk, dv, kmask, B, nh, nkv, Sq, Skv, hd, q_bs, q_ss,
+                             k_bs, k_ss, v_bs, v_ss, o_bs, o_ss, do_bs, do_ss, dk_bs, dk_ss, dv_bs, dv_ss, scale, causal,
+                             ST(stream));
+}
+int cb_act_fwd(const void* x, void* y, int64_t n, int act, void* stream) {
+  return cb::act_fwd_launch(x, y, n, act, ST(stream));
+}
+int cb_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int act, void* stream) {
+  return cb::act_bwd_launch(dy, x, dx, n, act, ST(stream));
+}
+int cb_swiglu_fwd(const void* gate, const void* up, void* out, int64_t rows, int I, int64_t ld_in, int64_t ld_out,
+                  void* stream) {
+  return cb::swiglu_fwd_launch(gate, up, out, rows, I, ld_in, ld_out, ST(stream));
+}
+int cb_swiglu_bwd(const void* dout, const void* gate, const void* up, void* dgate, void* dup, int64_t rows, int I,
+                  int64_t ld_in, int64_t ld_dout, int64_t ld_dgu, void* stream) {
+  return cb::swiglu_bwd_launch(dout, gate, up, dgate, dup, rows, I, ld_in, ld_dout, ld_dgu, ST(stream));
+}
+int cb_rope(void* buf, const int64_t* pos, const float* cos_t, const float* sin_t, int64_t rows, int n_heads, int hd,
+            int64_t ld, int max_pos, int inverse, void* stream) {
+  return cb::rope_launch(buf, reinterpret_cast<const long long*>(pos), cos_t, sin_t, rows, n_heads, hd, ld, max_pos,
+                         inverse, ST(stream));
+}
+int cb_embed_splice(const int64_t* ids, const int32_t* img_start, const void* embed, const void* img,
+                    const void* newline, void* out, int B, int S, int H, int q_side, int64_t vocab, void* stream) {
+  return cb::embed_splice_launch(reinterpret_cast<const long long*>(ids), img_start, embed, img, newline, out, B, S, H,
+                                 q_side, vocab, ST(stream));
+}
+int cb_embed_splice_bwd(const void* dout, const int64_t* ids, const int32_t* img_start, void* d_embed, void* d_img,
+                        void* d_newline_rows, int B, int S, int H, int q_side, int64_t vocab, void* stream) {
+  return cb::embed_splice_bwd_launch(dout, reinterpret_cast<const long long*>(ids), img_start, d_embed, d_img,
+                                     d_newline_rows, B, S, H, q_side, vocab, ST(stream));
+}
+int cb_add_pos_tokens(const void* patch, const void* cls, const void* pos, void* out, int B, int N, int C,
+                      void* stream) {
+  return cb::add_pos_tokens_launch(patch, cls, pos, out, B, N, C, ST(stream));
+}
+int cb_bilinear(const void* in, void* out, int B, int h, int w, int th, int tw, int C, int64_t in_bs, int64_t out_bs,
+                int out_ld, int out_col0, void* stream) {
+  return cb::bilinear_launch(in, out, B, h, w, th, tw, C, in_bs, out_bs, out_ld, out_col0, ST(stream));
+}
+int cb_patchify_nchw(const void* img, void* out, int B, int Cin, int R, int p, int Kpad, void* stream) {
+  return cb::patchify_nchw_launch(img, out, B, Cin, R, p, Kpad, ST(stream));
+}
+int cb_patchify_nhwc(const void* in, void* out, int B, int H, int W, int C, int p, void* stream) {
+  return cb::patchify_nhwc_launch(in, out, B, H, W, C, p, ST(stream));
+}
+int cb_dwconv7(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int C, void* stream) {
+  return cb::dwconv7_launch(in, w, bias, out, B, H, W, C, ST(stream));
+}
+int cb_add_inplace(void* dst, const void* src, int64_t n, void* stream) {
+  return cb::add_inplace_launch(dst, src, n, ST(stream));
+}
+int cb_group_colsum(const void* x, void* out_bf16, float* out_f32, int groups, int64_t rows_per_group, int C,
+                    float scale, int accumulate, void* stream) {
+  return cb::group_colsum_launch(x, out_bf16, out_f32, groups, rows_per_group, C, scale, accumulate, ST(stream));
+}
+int cb_group_broadcast(const void* dmean, void* dx, int groups, int64_t rows_per_group, int C, float scale,
+                       int accumulate, void* stream) {
+  return cb::group_broadcast_launch(dmean, dx, groups, rows_per_group, C, scale, accumulate, ST(stream));
+}
+int cb_pos_grad(const void* dx, void* dpos, int B, int side, int r, int C, int accumulate, void* stream) {
+  return cb::pos_grad_launch(dx, dpos, B, side, r, C, accumulate, ST(stream));
+}
+int cb_f32_to_bf16(const float* in, void* out, int64_t rows, int cols, int64_t out_ld, float scale, void* stream) {
+  return cb::f32_to_bf16_launch(in, out, rows, cols, out_ld, scale, ST(stream));
+}
+int cb_cross_entropy(void* logits, const int64_t* labels, float* loss_rows, float* loss_acc, int64_t rows, int64_t V,
+                     int64_t ld, float grad_scale, int write_grad, int64_t ignore_index, void* stream) {
+  return cb::cross_entropy_launch(logits, reinterpret_cast<const long long*>(labels), loss_rows, loss_acc, rows, V, ld,
+                                  grad_scale, write_grad, ignore_index, ST(stream));
+}
+int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
+             float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  return cb::adamw_launch(p, m, v, g, p16, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, ST(stream));
+}
 
 }  // extern "C"

@@ -186,3 +186,236 @@ def rmsnorm_bwd(dy, x, gamma, rstd):
                                     ws.numel(), rows, C_, stream())
     check(rc, "cb_rmsnorm_bwd")
     return dx.view(x.shape), dgamma
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def _bshd_strides(t, hd):
+    """t is a [B, S, heads, hd] view (possibly a slice of a packed QKV buffer) with unit stride on hd and
+    heads packed at stride hd."""
+    if t.dim() != 4 or t.stride(3) != 1 or (t.shape[2] > 1 and t.stride(2) != hd):
+        raise ValueError(f"attention operand must be [B,S,heads,hd] with packed heads, got strides {t.stride()}")
+    return t.stride(0), t.stride(1)
+
+
+def attn_fwd(q, k, v, *, causal: bool, kmask=None, scale: float | None = None, need_lse: bool = False, out=None):
+    """q [B,Sq,nh,hd], k/v [B,Skv,nkv,hd] (views are fine) -> o [B,Sq,nh,hd] contiguous (+ lse [B,nh,Sq])."""
+    _require_cuda_bf16(q, k, v)
+    B, Sq, nh, hd = q.shape
+    Skv, nkv = k.shape[1], k.shape[2]
+    if scale is None:
+        scale = hd ** -0.5
+    o = out if out is not None else torch.empty((B, Sq, nh, hd), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B, nh, Sq), dtype=torch.float32, device=q.device) if need_lse else None
+    qb, qs = _bshd_strides(q, hd)
+    kb, ks = _bshd_strides(k, hd)
+    vb, vs_ = _bshd_strides(v, hd)
+    ob, os_ = _bshd_strides(o, hd)
+    if kmask is not None:
+        kmask = kmask.contiguous()
+        kmask = kmask.view(torch.uint8) if kmask.dtype == torch.bool else kmask.to(torch.uint8)
+    rc = _lib.load().cb_attn_fwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), ptr(kmask), B, nh, nkv, Sq, Skv, hd,
+                                 qb, qs, kb, ks, vb, vs_, ob, os_, float(scale), int(causal), stream())
+    check(rc, "cb_attn_fwd")
+    return (o, lse) if need_lse else o
+
+
+def attn_bwd(q, k, v, o, do, lse, *, causal: bool, kmask=None, scale: float | None = None, dq=None, dk=None, dv=None):
+    """Returns dq [B,Sq,nh,hd], dk, dv [B,Skv,nkv,hd] (bf16).  dq/dk/dv may be preallocated (strided views ok)."""
+    _require_cuda_bf16(q, k, v, o, do)
+    B, Sq, nh, hd = q.shape
+    Skv, nkv = k.shape[1], k.shape[2]
+    if scale is None:
+        scale = hd ** -0.5
+    dev = q.device
+    delta = torch.empty((B, nh, Sq), dtype=torch.float32, device=dev)
+    dq_acc = torch.zeros((B, Sq, nh, hd), dtype=torch.float32, device=dev)
+    dk = dk if dk is not None else torch.empty((B, Skv, nkv, hd), dtype=torch.bfloat16, device=dev)
+    dv = dv if dv is not None else torch.empty((B, Skv, nkv, hd), dtype=torch.bfloat16, device=dev)
+    qb, qs = _bshd_strides(q, hd)
+    kb, ks = _bshd_strides(k, hd)
+    vb, vs_ = _bshd_strides(v, hd)
+    ob, os_ = _bshd_strides(o, hd)
+    dob, dos = _bshd_strides(do, hd)
+    dkb, dks = _bshd_strides(dk, hd)
+    dvb, dvs = _bshd_strides(dv, hd)
+    if kmask is not None:
+        kmask = kmask.contiguous()
+        kmask = kmask.view(torch.uint8) if kmask.dtype == torch.bool else kmask.to(torch.uint8)
+    rc = _lib.load().cb_attn_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(delta), ptr(dq_acc), ptr(dk),
+                                 ptr(dv), ptr(kmask), B, nh, nkv, Sq, Skv, hd, qb, qs, kb, ks, vb, vs_, ob, os_, dob, dos,
+                                 dkb, dks, dvb, dvs, float(scale), int(causal), stream())
+    check(rc, "cb_attn_bwd")
+    if dq is None:
+        dq = torch.empty((B, Sq, nh, hd), dtype=torch.bfloat16, device=dev)
+    # dq may be a [B,Sq,nh,hd] view into a packed dQKV buffer: rows (b,s) at stride dq.stride(1)
+    assert dq.stride(3) == 1 and dq.stride(2) == hd and dq.stride(0) == Sq * dq.stride(1)
+    f32_to_bf16(dq_acc, dq, scale, cols=nh * hd, out_ld=dq.stride(1))
+    return dq, dk, dv
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise / gather / reductions
+# ------------------------------------------------------------------------------------------------
+def act_fwd(x, act):
+    _require_cuda_bf16(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(_lib.load().cb_act_fwd(ptr(x), ptr(y), x.numel(), ACT[act], stream()), "cb_act_fwd")
+    return y
+
+
+def act_bwd(dy, x, act):
+    _require_cuda_bf16(dy, x)
+    dy, x = dy.contiguous(), x.contiguous()
+    dx = torch.empty_like(x)
+    check(_lib.load().cb_act_bwd(ptr(dy), ptr(x), ptr(dx), x.numel(), ACT[act], stream()), "cb_act_bwd")
+    return dx
+
+
+def swiglu_fwd(gate, up):
+    """gate/up: [rows, I] views with a common row stride (e.g. the two halves of a fused [rows, 2I] buffer)."""
+    _require_cuda_bf16(gate, up)
+    rows, I = gate.shape
+    assert gate.stride(1) == 1 and up.stride(1) == 1 and gate.stride(0) == up.stride(0)
+    out = torch.empty((rows, I), dtype=torch.bfloat16, device=gate.device)
+    check(_lib.load().cb_swiglu_fwd(ptr(gate), ptr(up), ptr(out), rows, I, gate.stride(0), I, stream()), "cb_swiglu_fwd")
+    return out
+
+
+def swiglu_bwd(dout, gate, up, dgate, dup):
+    _require_cuda_bf16(dout, gate, up, dgate, dup)
+    rows, I = gate.shape
+    assert dgate.stride(0) == dup.stride(0) and dout.stride(1) == 1
+    check(_lib.load().cb_swiglu_bwd(ptr(dout), ptr(gate), ptr(up), ptr(dgate), ptr(dup), rows, I, gate.stride(0),
+                                    dout.stride(0), dgate.stride(0), stream()), "cb_swiglu_bwd")
+
+
+def rope_(buf, pos, cos_t, sin_t, n_heads: int, hd: int, inverse: bool = False):
+    """In-place RoPE on the first n_heads heads of each row of buf [rows, ld]."""
+    _require_cuda_bf16(buf)
+    assert buf.dim() == 2 and buf.stride(1) == 1 and pos.dtype == torch.int64 and pos.is_contiguous()
+    check(_lib.load().cb_rope(ptr(buf), ptr(pos), ptr(cos_t), ptr(sin_t), buf.shape[0], n_heads, hd, buf.stride(0),
+                              cos_t.shape[0], int(inverse), stream()), "cb_rope")
+    return buf
+
+
+def embed_splice(ids, img_start, embed, img, newline, q_side: int):
+    B, S = ids.shape
+    H = embed.shape[1]
+    out = torch.empty((B, S, H), dtype=torch.bfloat16, device=embed.device)
+    check(_lib.load().cb_embed_splice(ptr(ids), ptr(img_start), ptr(embed), ptr(img), ptr(newline), ptr(out), B, S, H,
+                                      q_side, embed.shape[0], stream()), "cb_embed_splice")
+    return out
+
+
+def embed_splice_bwd(dout, ids, img_start, d_embed, q_side: int, has_img: bool):
+    B, S, H = dout.shape
+    dev = dout.device
+    d_img = torch.empty((B, q_side * q_side, H), dtype=torch.bfloat16, device=dev) if has_img else None
+    d_nl = torch.empty((B * q_side, H), dtype=torch.bfloat16, device=dev) if has_img else None
+    vocab = d_embed.shape[0] if d_embed is not None else 0
+    check(_lib.load().cb_embed_splice_bwd(ptr(dout), ptr(ids), ptr(img_start), ptr(d_embed), ptr(d_img), ptr(d_nl), B, S,
+                                          H, q_side, vocab, stream()), "cb_embed_splice_bwd")
+    return d_img, d_nl
+
+
+def add_pos_tokens(patch, cls, pos):
+    B, N, C_ = patch.shape
+    T = N + (1 if cls is not None else 0)
+    out = torch.empty((B, T, C_), dtype=torch.bfloat16, device=patch.device)
+    check(_lib.load().cb_add_pos_tokens(ptr(patch), ptr(cls), ptr(pos), ptr(out), B, N, C_, stream()), "cb_add_pos_tokens")
+    return out
+
+
+def bilinear(x, h: int, w: int, th: int, tw: int, *, in_bs=None, out=None, out_ld=None, out_col0: int = 0):
+    """x: [B, >=h*w, C] token grid (first h*w rows of each batch used, e.g. after skipping CLS via a view)."""
+    B, C_ = x.shape[0], x.shape[-1]
+    in_bs = x.stride(0) if in_bs is None else in_bs
+    if out is None:
+        out = torch.empty((B, th * tw, C_), dtype=torch.bfloat16, device=x.device)
+    out_ld = out.stride(1) if out_ld is None else out_ld
+    check(_lib.load().cb_bilinear(ptr(x), ptr(out), B, h, w, th, tw, C_, in_bs, out.stride(0), out_ld, out_col0, stream()),
+          "cb_bilinear")
+    return out
+
+
+def patchify_nchw(img, p: int):
+    B, Cin, R, _ = img.shape
+    img = img.contiguous()
+    K = Cin * p * p
+    Kpad = (K + 7) // 8 * 8
+    g = R // p
+    out = torch.empty((B * g * g, Kpad), dtype=torch.bfloat16, device=img.device)
+    check(_lib.load().cb_patchify_nchw(ptr(img), ptr(out), B, Cin, R, p, Kpad, stream()), "cb_patchify_nchw")
+    return out
+
+
+def patchify_nhwc(x, p: int):
+    B, H, W, C_ = x.shape
+    out = torch.empty((B * (H // p) * (W // p), p * p * C_), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().cb_patchify_nhwc(ptr(x), ptr(out), B, H, W, C_, p, stream()), "cb_patchify_nhwc")
+    return out
+
+
+def dwconv7(x, w, bias):
+    B, H, W, C_ = x.shape
+    out = torch.empty_like(x)
+    check(_lib.load().cb_dwconv7(ptr(x), ptr(w), ptr(bias), ptr(out), B, H, W, C_, stream()), "cb_dwconv7")
+    return out
+
+
+def add_(dst, src):
+    assert dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
+    check(_lib.load().cb_add_inplace(ptr(dst), ptr(src), dst.numel(), stream()), "cb_add_inplace")
+    return dst
+
+
+def group_colsum(x, groups: int, scale: float = 1.0, out=None, accumulate: bool = False, fp32: bool = False):
+    C_ = x.shape[-1]
+    x2 = x.reshape(-1, C_)
+    rpg = x2.shape[0] // groups
+    if out is None:
+        out = torch.empty((groups, C_), dtype=torch.float32 if fp32 else torch.bfloat16, device=x.device)
+    ob, of = (None, out) if out.dtype == torch.float32 else (out, None)
+    check(_lib.load().cb_group_colsum(ptr(x2), ptr(ob), ptr(of), groups, rpg, C_, float(scale), int(accumulate), stream()),
+          "cb_group_colsum")
+    return out
+
+
+def group_broadcast(dmean, rows_per_group: int, scale: float, out=None, accumulate: bool = False):
+    groups, C_ = dmean.shape
+    if out is None:
+        out = torch.empty((groups * rows_per_group, C_), dtype=torch.bfloat16, device=dmean.device)
+    check(_lib.load().cb_group_broadcast(ptr(dmean), ptr(out), groups, rows_per_group, C_, float(scale), int(accumulate),
+                                         stream()), "cb_group_broadcast")
+    return out
+
+
+def pos_grad(dx, B: int, side: int, r: int, out=None, accumulate: bool = False):
+    C_ = dx.shape[-1]
+    if out is None:
+        out = torch.empty((r * r, C_), dtype=torch.bfloat16, device=dx.device)
+    check(_lib.load().cb_pos_grad(ptr(dx), ptr(out), B, side, r, C_, int(accumulate), stream()), "cb_pos_grad")
+    return out
+
+
+def f32_to_bf16(src, dst, scale: float = 1.0, cols: int | None = None, out_ld: int | None = None):
+    """src fp32 contiguous viewed as [rows, cols]; dst bf16 rows at stride out_ld."""
+    cols = src.shape[-1] if cols is None else cols
+    rows = src.numel() // cols
+    out_ld = cols if out_ld is None else out_ld
+    check(_lib.load().cb_f32_to_bf16(ptr(src), ptr(dst), rows, cols, out_ld, float(scale), stream()), "cb_f32_to_bf16")
+    return dst
+
+
+def cross_entropy(logits, labels, loss_rows, loss_acc, grad_scale: float, write_grad: bool, ignore_index: int = -100):
+    rows, V = logits.shape
+    check(_lib.load().cb_cross_entropy(ptr(logits), ptr(labels), ptr(loss_rows), ptr(loss_acc), rows, V, logits.stride(0),
+                                       float(grad_scale), int(write_grad), ignore_index, stream()), "cb_cross_entropy")
+
+
+def adamw(p32, m, v, g16, p16, lr, beta1, beta2, eps, wd, step: int, grad_scale: float = 1.0):
+    check(_lib.load().cb_adamw(ptr(p32), ptr(m), ptr(v), ptr(g16), ptr(p16), p32.numel(), float(lr), float(beta1),
+                               float(beta2), float(eps), float(wd), int(step), float(grad_scale), stream()), "cb_adamw")

@@ -91,6 +91,75 @@ int cb_rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float
                    void* stream);
 int64_t cb_norm_bwd_workspace_floats(int64_t rows, int C);
 
+/* ---- softmax attention: tcgen05 flash attention ------------------------------------------------
+ * q/k/v/o element (b, s, head, d) lives at base + b*bs + s*ss + head*hd + d (element strides), so the packed
+ * QKV GEMM output is consumed in place.  nh % nkv == 0 (GQA).  kmask [B, Skv] bool (1 byte, 1 = attend) or NULL.
+ * causal: key k visible to query i iff k <= i + (Skv - Sq).  lse [B, nh, Sq] fp32 (log2 domain) may be NULL.
+ * Replaces torch SDPA inside HF CLIPAttention / Dinov2SelfAttention / timm Attention (clip_encoder.py:104,
+ * dino_encoder.py:159, siglip_encoder.py:97) and HF LlamaSdpaAttention with the 4-D causal+padding mask of
+ * cambrian_llama.py:123-128.  head_dim: any multiple of 8 up to 128 (fwd); 64 or 128 (bwd). */
+int cb_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const void* kmask, int B, int nh,
+                int nkv, int Sq, int Skv, int hd, int64_t q_bs, int64_t q_ss, int64_t k_bs, int64_t k_ss,
+                int64_t v_bs, int64_t v_ss, int64_t o_bs, int64_t o_ss, float scale, int causal, void* stream);
+/* delta [B, nh, Sq] fp32 scratch; dq_acc [B, Sq, nh, hd] fp32 ZERO-INITIALISED by the caller, receives the
+ * unscaled sum dS K (multiply by `scale` when converting, cb_f32_to_bf16); dk/dv written (bf16, strided). */
+int cb_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                float* delta, float* dq_acc, void* dk, void* dv, const void* kmask, int B, int nh, int nkv, int Sq,
+                int Skv, int hd, int64_t q_bs, int64_t q_ss, int64_t k_bs, int64_t k_ss, int64_t v_bs, int64_t v_ss,
+                int64_t o_bs, int64_t o_ss, int64_t do_bs, int64_t do_ss, int64_t dk_bs, int64_t dk_ss,
+                int64_t dv_bs, int64_t dv_ss, float scale, int causal, void* stream);
+
+/* ---- elementwise / gather / reduction kernels (HBM-bound) -------------------------------------- */
+/* y = act(x), dx = dy * act'(x); n elements (n % 8 == 0).  nn.GELU of vision_sampler.py:241, cambrian_arch.py:49,56 */
+int cb_act_fwd(const void* x, void* y, int64_t n, int act, void* stream);
+int cb_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int act, void* stream);
+/* out = silu(gate) * up (HF LlamaMLP); gate/up rows may live in one [rows, 2I] buffer (ld_in) */
+int cb_swiglu_fwd(const void* gate, const void* up, void* out, int64_t rows, int I, int64_t ld_in, int64_t ld_out,
+                  void* stream);
+int cb_swiglu_bwd(const void* dout, const void* gate, const void* up, void* dgate, void* dup, int64_t rows, int I,
+                  int64_t ld_in, int64_t ld_dout, int64_t ld_dgu, void* stream);
+/* in-place rotary embedding of the first n_heads heads of each row of a packed [rows, ld] buffer;
+ * pos int64 [rows]; cos/sin fp32 [max_pos, hd/2]; inverse = 1 applies the transpose (backward).
+ * HF apply_rotary_pos_emb as used by LlamaAttention (cambrian_llama.py:142-164). */
+int cb_rope(void* buf, const int64_t* pos, const float* cos_t, const float* sin_t, int64_t rows, int n_heads, int hd,
+            int64_t ld, int max_pos, int inverse, void* stream);
+/* inputs_embeds [B,S,H]: embed_tokens gather + image-span replace + image_newline column
+ * (cambrian_arch.py:413-420, :457-490).  img [B, q*q, H] or NULL (text only); img_start int32 [B] (<0: no image) */
+int cb_embed_splice(const int64_t* ids, const int32_t* img_start, const void* embed, const void* img,
+                    const void* newline, void* out, int B, int S, int H, int q_side, int64_t vocab, void* stream);
+int cb_embed_splice_bwd(const void* dout, const int64_t* ids, const int32_t* img_start, void* d_embed, void* d_img,
+                        void* d_newline_rows, int B, int S, int H, int q_side, int64_t vocab, void* stream);
+/* ViT token assembly: out[b] = [cls + pos[0]] ++ (patch[b] + pos[1:])  (cls may be NULL: SigLIP) */
+int cb_add_pos_tokens(const void* patch, const void* cls, const void* pos, void* out, int B, int N, int C,
+                      void* stream);
+/* fp32 bilinear token-grid resize, align_corners=False (clip_encoder.py:83-88 and siblings, cambrian_arch.py:397-400)
+ * in: [B, h, w, C] rows at in_bs batch stride; out row (b, oy, ox) at out + b*out_bs + (oy*tw+ox)*out_ld + out_col0 */
+int cb_bilinear(const void* in, void* out, int B, int h, int w, int th, int tw, int C, int64_t in_bs, int64_t out_bs,
+                int out_ld, int out_col0, void* stream);
+/* im2col for strided patch convolutions feeding cb_gemm_bf16 */
+int cb_patchify_nchw(const void* img, void* out, int B, int Cin, int R, int p, int Kpad, void* stream);
+int cb_patchify_nhwc(const void* in, void* out, int B, int H, int W, int C, int p, void* stream);
+/* depthwise 7x7 conv, NHWC, weights [7,7,C] (timm ConvNeXtBlock.conv_dw via clip_convnext_encoder.py:121-144) */
+int cb_dwconv7(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int C, void* stream);
+int cb_add_inplace(void* dst, const void* src, int64_t n, void* stream);
+/* out[g, c] = scale * sum_r x[g*rows_per_group + r, c]; either output may be NULL (cambrian_arch.py:377 mean; bias grads) */
+int cb_group_colsum(const void* x, void* out_bf16, float* out_f32, int groups, int64_t rows_per_group, int C,
+                    float scale, int accumulate, void* stream);
+int cb_group_broadcast(const void* dmean, void* dx, int groups, int64_t rows_per_group, int C, float scale,
+                       int accumulate, void* stream);
+/* d pos_embed [r*r, C] from the gradient of the (x + pos) rows on the natural grid layout */
+int cb_pos_grad(const void* dx, void* dpos, int B, int side, int r, int C, int accumulate, void* stream);
+/* fp32 [rows, cols] contiguous -> bf16 rows at stride out_ld, times scale (dQ of cb_attn_bwd into a packed dQKV buffer) */
+int cb_f32_to_bf16(const float* in, void* out, int64_t rows, int cols, int64_t out_ld, float scale, void* stream);
+/* per-row cross entropy on bf16 logits [rows, V] (fp32 math, cambrian_llama.py:408-422); loss_rows [rows];
+ * loss_acc (may be NULL) += {sum of losses, number of non-ignored rows}; write_grad overwrites the logits in place
+ * with (softmax - onehot) * grad_scale. */
+int cb_cross_entropy(void* logits, const int64_t* labels, float* loss_rows, float* loss_acc, int64_t rows, int64_t V,
+                     int64_t ld, float grad_scale, int write_grad, int64_t ignore_index, void* stream);
+/* AdamW on fp32 master weights / moments with bf16 gradients, writing the bf16 compute copy */
+int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
+             float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
