@@ -24,13 +24,13 @@ SIGNATURES = {
     "cb_sm_count": (_i, []),
     "cb_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i, _i,
                           _vp, _vp, _vp, _i64, _i64, _f, _i, _i, _i, _i, _vp]),
-    "cb_sva_window_attn_fwd": (_i, [_vp, _vp, _vp, _i, _vpp, _vpp, _vpp, _ip, _i, _i, _i, _vp]),
+    "cb_sva_window_attn_fwd": (_i, [_vp, _vp, _vp, _i, _vpp, _vpp, _vpp, _ip, _i, _i, _i, _i, _vp]),
     "cb_sva_window_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vpp, _vpp, _vpp, _vpp, _vpp, _ip,
-                                    _i, _i, _i, _vp]),
+                                    _i, _i, _i, _i, _vp]),
     "cb_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _vp, _i, _i, _vp]),
-    "cb_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _vp, _i, _i, _vp]),
+    "cb_layernorm_bwd": (_i, [_vp] * 10 + [_i64, _i64, _i, _vp, _i, _i, _vp]),
     "cb_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _f, _i, _vp]),
-    "cb_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _vp]),
+    "cb_rmsnorm_bwd": (_i, [_vp] * 8 + [_i64, _i64, _i, _vp]),
     "cb_norm_bwd_workspace_floats": (_i64, [_i64, _i]),
     "cb_attn_fwd": (_i, [_vp] * 6 + [_i] * 6 + [_i64] * 8 + [_f, _i, _vp]),
     "cb_attn_bwd": (_i, [_vp] * 11 + [_i] * 6 + [_i64] * 14 + [_f, _i, _vp]),

@@ -1,0 +1,456 @@
+"""Hand-scheduled forward/backward of the hot-path blocks, exposed as torch.autograd.Functions.
+
+Each Function launches only kernels of libcambrian_b200.so (through `ops`); torch supplies tensor storage and the
+autograd tape between blocks.  Blocks are coarse on purpose (a whole SVA layer, a whole decoder layer) so that every
+gradient fan-in is an explicit fused kernel (`dres` of the norm backward, GEMM residual epilogue) instead of an
+autograd-inserted add.
+
+Weight gradients: if a parameter carries a `main_grad` tensor (set by `cambrian_b200.engine.TrainEngine`, a view into
+the flat bf16 gradient buffer that the optimizer and the NCCL all-reduce consume), the dW GEMM accumulates straight
+into it and autograd receives None; otherwise the gradient tensor is returned to autograd as usual.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def wgrad(param: torch.Tensor, dy2d: torch.Tensor, x2d: torch.Tensor, out_view=None):
+    """dW[N_out, K_in] = dy2d[rows, N_out]^T @ x2d[rows, K_in].  `out_view` selects a column slice of the gradient
+    (used for proj_in's two halves)."""
+    mg = getattr(param, "main_grad", None)
+    if mg is not None:
+        tgt = mg if out_view is None else out_view(mg)
+        fresh = getattr(param, "_cb_fresh", None)
+        key = "all" if out_view is None else id(out_view)
+        first = fresh is not None and key not in fresh
+        ops.gemm(dy2d, x2d, a_mn=True, b_mn=True, out=tgt, accumulate=not first)
+        if fresh is not None:
+            fresh.add(key)
+        return None
+    return ops.gemm(dy2d, x2d, a_mn=True, b_mn=True)
+
+
+def vgrad(param: torch.Tensor, g: torch.Tensor):
+    """Gradient of a vector/small parameter computed by a reduction kernel (bf16)."""
+    mg = getattr(param, "main_grad", None)
+    if mg is not None:
+        fresh = getattr(param, "_cb_fresh", None)
+        if fresh is not None and "all" not in fresh:
+            mg.view(-1).copy_(g.view(-1))  # first write of the step (tiny tensors: LN affine, biases)
+            fresh.add("all")
+        else:
+            ops.add_(mg.view(-1), g.contiguous().view(-1)) if mg.numel() % 8 == 0 else mg.add_(g.view_as(mg))
+        return None
+    return g
+
+
+def _merge_wgrad(parts):
+    """Assemble a full-weight gradient from column blocks when no main_grad buffer exists."""
+    return torch.cat(parts, dim=1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Linear (+ bias) and small projector MLPs (mm_projector, mm_projector_aux)
+# ------------------------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        ctx.params = (weight, bias)
+        return ops.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        w_param, b_param = ctx.params
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        x2 = x.reshape(-1, x.shape[-1])
+        dx = ops.gemm(dy2, weight, b_mn=True).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = wgrad(w_param, dy2, x2) if ctx.needs_input_grad[1] else None
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = vgrad(b_param, ops.group_colsum(dy2, 1).view(-1))
+        return dx, dw, db
+
+
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        ctx.save_for_backward(x)
+        ctx.act = act
+        return ops.act_fwd(x, act)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.act_bwd(dy.contiguous(), x, ctx.act), None
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        y, mean, rstd = ops.layernorm_fwd(x, weight, bias, eps, save_stats=True)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.params = (weight, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(dy.contiguous(), x, weight, mean, rstd)
+        return dx, vgrad(ctx.params[0], dg), vgrad(ctx.params[1], db), None
+
+
+class RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, eps, hf_cast):
+        y, rstd = ops.rmsnorm_fwd(x, weight, eps, hf_cast, save_stats=True)
+        ctx.save_for_backward(x, weight, rstd)
+        ctx.param = weight
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, rstd = ctx.saved_tensors
+        dx, dg = ops.rmsnorm_bwd(dy.contiguous(), x, weight, rstd)
+        return dx, vgrad(ctx.param, dg), None, None
+
+
+class MeanTokensFn(torch.autograd.Function):
+    """global context = mean over tokens (cambrian_arch.py:377): [B, N, C] -> [B, C]."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, N, C = x.shape
+        ctx.shape = (B, N, C)
+        return ops.group_colsum(x.contiguous(), B, 1.0 / N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, N, C = ctx.shape
+        return ops.group_broadcast(dy.contiguous(), N, 1.0 / N).view(B, N, C)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SVA layer (VisionCrossAttentionLayer.forward, vision_sampler.py:270-327)
+# ------------------------------------------------------------------------------------------------------------------
+class SVALayerFn(torch.autograd.Function):
+    """args: meta, queries [N,Dq], ctx [N,Dc], feats_0..T-1, then the layer's parameters in `meta['names']` order.
+
+    meta = dict(T, rs, masks (list of bool tensors or None), natural=(B, q_side) or None (window-rearranged inputs),
+                params (list of nn.Parameter in the same order as the tensor args))
+    """
+
+    @staticmethod
+    def forward(ctx, meta, queries, ctxf, *tensors):
+        T, rs = meta["T"], meta["rs"]
+        feats = [t.reshape(-1, t.shape[-1]) for t in tensors[:T]]
+        P = dict(zip(meta["names"], tensors[T:]))
+        N, D = queries.shape
+        nat = meta["natural"]
+        windowed = nat is None
+        B, q_side = (N, 1) if windowed else nat
+        masks = meta["masks"]
+
+        ctxp = ops.gemm(ctxf, P["proj_context"])
+        t32 = ops.gemm(queries, P["proj_in"][:, :D], out_dtype=torch.float32)
+        ops.gemm(ctxp, P["proj_in"][:, D:], out=t32, accumulate=True)
+        qin = ops.f32_to_bf16(t32, torch.empty((N, t32.shape[1]), dtype=torch.bfloat16, device=queries.device))
+        qn, mq, rq = ops.layernorm_fwd(qin, P["q_ln_w"], P["q_ln_b"], 1e-5, save_stats=True)
+        Q = ops.gemm(qn, P["q_w"])
+        kins, vins, stats, Ks, Vs = [], [], [], [], []
+        for i in range(T):
+            r = rs[i]
+            pos = P.get(f"pos_embed_{i}") if r > 1 else None
+            side = 0 if windowed else r * q_side
+            kin, mean, rstd = ops.layernorm_fwd(feats[i], P[f"k_ln_w_{i}"], P[f"k_ln_b_{i}"], 1e-5, pos=pos, side=side, r=r,
+                                                save_stats=True)
+            vin = ops.layernorm_fwd(feats[i], P[f"v_ln_w_{i}"], P[f"v_ln_b_{i}"], 1e-5, pos=pos, side=side, r=r)
+            kins.append(kin)
+            vins.append(vin)
+            stats += [mean, rstd]
+            Ks.append(ops.gemm(kin, P[f"k_w_{i}"]))
+            Vs.append(ops.gemm(vin, P[f"v_w_{i}"]))
+        A, lse = ops.sva_window_attn_fwd(Q, Ks, Vs, masks, rs, B, q_side, need_lse=True, windowed=windowed)
+        q2 = ops.gemm(A, P["o_w"], residual=qin)
+        q3, m3, r3 = ops.layernorm_fwd(q2, P["norm_w"], P["norm_b"], 1e-5, save_stats=True)
+        h1 = ops.gemm(q3, P["out1_w"])
+        h2 = ops.act_fwd(h1, "gelu")
+        out = ops.gemm(h2, P["out2_w"], residual=queries)
+
+        ctx.meta = meta
+        ctx.dims = (N, D, B, q_side, windowed)
+        ctx.nparams = len(meta["names"])
+        ctx.save_for_backward(queries, ctxf, ctxp, qin, mq, rq, qn, Q, A, lse, q2, m3, r3, q3, h1, h2,
+                              *feats, *kins, *vins, *stats, *Ks, *Vs, *tensors[T:])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        meta = ctx.meta
+        T, rs, masks = meta["T"], meta["rs"], meta["masks"]
+        N, D, B, q_side, windowed = ctx.dims
+        sv = ctx.saved_tensors
+        queries, ctxf, ctxp, qin, mq, rq, qn, Q, A, lse, q2, m3, r3, q3, h1, h2 = sv[:16]
+        o = 16
+        feats = sv[o:o + T]; o += T
+        kins = sv[o:o + T]; o += T
+        vins = sv[o:o + T]; o += T
+        stats = sv[o:o + 2 * T]; o += 2 * T
+        Ks = sv[o:o + T]; o += T
+        Vs = sv[o:o + T]; o += T
+        P = dict(zip(meta["names"], sv[o:]))
+        prm = dict(zip(meta["names"], meta["params"]))
+        g = {}
+        dout = dout.contiguous()
+
+        dh2 = ops.gemm(dout, P["out2_w"], b_mn=True)
+        g["out2_w"] = wgrad(prm["out2_w"], dout, h2)
+        dh1 = ops.act_bwd(dh2, h1, "gelu")
+        dq3 = ops.gemm(dh1, P["out1_w"], b_mn=True)
+        g["out1_w"] = wgrad(prm["out1_w"], dh1, q3)
+        dq2, dgn, dbn = ops.layernorm_bwd(dq3, q2, P["norm_w"], m3, r3)
+        g["norm_w"], g["norm_b"] = vgrad(prm["norm_w"], dgn), vgrad(prm["norm_b"], dbn)
+        dA = ops.gemm(dq2, P["o_w"], b_mn=True)
+        g["o_w"] = wgrad(prm["o_w"], dq2, A)
+        dQ, dKs, dVs = ops.sva_window_attn_bwd(Q, A, dA, lse, list(Ks), list(Vs), masks, rs, B, q_side, windowed=windowed)
+        dqn = ops.gemm(dQ, P["q_w"], b_mn=True)
+        g["q_w"] = wgrad(prm["q_w"], dQ, qn)
+        dqin, dgq, dbq = ops.layernorm_bwd(dqn, qin, P["q_ln_w"], mq, rq, dres=dq2)
+        g["q_ln_w"], g["q_ln_b"] = vgrad(prm["q_ln_w"], dgq), vgrad(prm["q_ln_b"], dbq)
+        dfeats = []
+        for i in range(T):
+            r = rs[i]
+            pos = P.get(f"pos_embed_{i}") if r > 1 else None
+            side = 0 if windowed else r * q_side
+            mean, rstd = stats[2 * i], stats[2 * i + 1]
+            dkin = ops.gemm(dKs[i], P[f"k_w_{i}"], b_mn=True)
+            g[f"k_w_{i}"] = wgrad(prm[f"k_w_{i}"], dKs[i], kins[i])
+            dvin = ops.gemm(dVs[i], P[f"v_w_{i}"], b_mn=True)
+            g[f"v_w_{i}"] = wgrad(prm[f"v_w_{i}"], dVs[i], vins[i])
+            dxk, dgk, dbk = ops.layernorm_bwd(dkin, feats[i], P[f"k_ln_w_{i}"], mean, rstd, pos=pos, side=side, r=r)
+            dxv, dgv, dbv = ops.layernorm_bwd(dvin, feats[i], P[f"v_ln_w_{i}"], mean, rstd, pos=pos, side=side, r=r,
+                                              dres=dxk)
+            g[f"k_ln_w_{i}"], g[f"k_ln_b_{i}"] = vgrad(prm[f"k_ln_w_{i}"], dgk), vgrad(prm[f"k_ln_b_{i}"], dbk)
+            g[f"v_ln_w_{i}"], g[f"v_ln_b_{i}"] = vgrad(prm[f"v_ln_w_{i}"], dgv), vgrad(prm[f"v_ln_b_{i}"], dbv)
+            if r > 1:
+                if windowed:
+                    dp = ops.pos_grad(dxv, dxv.shape[0] // (r * r), r, r)
+                else:
+                    dp = ops.pos_grad(dxv, B, r * q_side, r)
+                g[f"pos_embed_{i}"] = vgrad(prm[f"pos_embed_{i}"], dp)
+            dfeats.append(dxv)
+        dqueries = ops.gemm(dqin, P["proj_in"][:, :D], b_mn=True, residual=dout)
+        dctxp = ops.gemm(dqin, P["proj_in"][:, D:], b_mn=True)
+        w_in = prm["proj_in"]
+        if getattr(w_in, "main_grad", None) is not None:
+            wgrad(w_in, dqin, queries, out_view=_slice_a(D))
+            wgrad(w_in, dqin, ctxp, out_view=_slice_b(D))
+            g["proj_in"] = None
+        else:
+            g["proj_in"] = torch.cat([ops.gemm(dqin, queries, a_mn=True, b_mn=True),
+                                      ops.gemm(dqin, ctxp, a_mn=True, b_mn=True)], 1)
+        dctx = ops.gemm(dctxp, P["proj_context"], b_mn=True)
+        g["proj_context"] = wgrad(prm["proj_context"], dctxp, ctxf)
+        tensors_in = meta["feat_shapes"]
+        dfeats = [d.view(s) for d, s in zip(dfeats, tensors_in)]
+        return (None, dqueries, dctx, *dfeats, *[g.get(n) for n in meta["names"]])
+
+
+_slice_cache: dict = {}
+
+
+def _slice_a(D):
+    k = ("a", D)
+    if k not in _slice_cache:
+        _slice_cache[k] = lambda t: t[:, :D]
+    return _slice_cache[k]
+
+
+def _slice_b(D):
+    k = ("b", D)
+    if k not in _slice_cache:
+        _slice_cache[k] = lambda t: t[:, D:]
+    return _slice_cache[k]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LLaMA decoder layer (HF LlamaDecoderLayer as called from cambrian_llama.py:142-166)
+# ------------------------------------------------------------------------------------------------------------------
+class DecoderLayerFn(torch.autograd.Function):
+    """x [B,S,H] -> x'.  Parameters: input_ln, qkv_w (fused [ (nh+2nkv)*hd, H ]), o_w, post_ln, gu_w (fused [2I, H]), down_w.
+
+    meta = dict(nh, nkv, hd, eps, hf_cast, cos, sin, pos (int64 [B*S]), kmask (bool [B,S] or None), params (6 Parameters),
+                recompute (bool: keep only x and redo the forward in backward — per-layer activation checkpointing))
+    """
+
+    @staticmethod
+    def _forward(meta, x, ln1, qkv_w, o_w, ln2, gu_w, down_w, keep):
+        B, S, H = x.shape
+        nh, nkv, hd = meta["nh"], meta["nkv"], meta["hd"]
+        rows = B * S
+        x2 = x.reshape(rows, H)
+        h, rstd1 = ops.rmsnorm_fwd(x2, ln1, meta["eps"], meta["hf_cast"], save_stats=True)
+        qkv = ops.gemm(h, qkv_w)
+        ops.rope_(qkv, meta["pos"], meta["cos"], meta["sin"], nh + nkv, hd)
+        q = qkv[:, : nh * hd].view(B, S, nh, hd)
+        k = qkv[:, nh * hd:(nh + nkv) * hd].view(B, S, nkv, hd)
+        v = qkv[:, (nh + nkv) * hd:].view(B, S, nkv, hd)
+        attn, lse = ops.attn_fwd(q, k, v, causal=True, kmask=meta["kmask"], need_lse=True)
+        attn2 = attn.view(rows, nh * hd)
+        x1 = ops.gemm(attn2, o_w, residual=x2)
+        h2, rstd2 = ops.rmsnorm_fwd(x1, ln2, meta["eps"], meta["hf_cast"], save_stats=True)
+        gu = ops.gemm(h2, gu_w)
+        I = gu_w.shape[0] // 2
+        act = ops.swiglu_fwd(gu[:, :I], gu[:, I:])
+        out = ops.gemm(act, down_w, residual=x1)
+        if keep:
+            return out.view(B, S, H), (rstd1, qkv, attn, lse, x1, rstd2, gu)
+        return out.view(B, S, H), None
+
+    @staticmethod
+    def forward(ctx, meta, x, ln1, qkv_w, o_w, ln2, gu_w, down_w):
+        keep = not meta["recompute"]
+        out, saved = DecoderLayerFn._forward(meta, x, ln1, qkv_w, o_w, ln2, gu_w, down_w, keep)
+        ctx.meta = meta
+        if keep:
+            ctx.save_for_backward(x, ln1, qkv_w, o_w, ln2, gu_w, down_w, *saved)
+        else:
+            ctx.save_for_backward(x, ln1, qkv_w, o_w, ln2, gu_w, down_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        meta = ctx.meta
+        sv = ctx.saved_tensors
+        x, ln1, qkv_w, o_w, ln2, gu_w, down_w = sv[:7]
+        if meta["recompute"]:
+            _, saved = DecoderLayerFn._forward(meta, x, ln1, qkv_w, o_w, ln2, gu_w, down_w, True)
+        else:
+            saved = sv[7:]
+        rstd1, qkv, attn, lse, x1, rstd2, gu = saved
+        p_ln1, p_qkv, p_o, p_ln2, p_gu, p_down = meta["params"]
+        B, S, H = x.shape
+        nh, nkv, hd = meta["nh"], meta["nkv"], meta["hd"]
+        rows = B * S
+        I = gu_w.shape[0] // 2
+        x2 = x.reshape(rows, H)
+        dx2 = dout.reshape(rows, H).contiguous()
+        # ---- MLP
+        h2 = ops.rmsnorm_fwd(x1, ln2, meta["eps"], meta["hf_cast"])       # cheap recompute (bandwidth only)
+        act = ops.swiglu_fwd(gu[:, :I], gu[:, I:])
+        dact = ops.gemm(dx2, down_w, b_mn=True)
+        g_down = wgrad(p_down, dx2, act)
+        del act
+        dgu = torch.empty_like(gu)
+        ops.swiglu_bwd(dact, gu[:, :I], gu[:, I:], dgu[:, :I], dgu[:, I:])
+        del dact
+        dh2 = ops.gemm(dgu, gu_w, b_mn=True)
+        g_gu = wgrad(p_gu, dgu, h2)
+        del dgu, h2
+        dx1, dg2 = ops.rmsnorm_bwd(dh2, x1, ln2, rstd2, dres=dx2)
+        g_ln2 = vgrad(p_ln2, dg2)
+        # ---- attention
+        attn2 = attn.view(rows, nh * hd)
+        dattn = ops.gemm(dx1, o_w, b_mn=True)
+        g_o = wgrad(p_o, dx1, attn2)
+        dqkv = torch.empty_like(qkv)
+        q = qkv[:, : nh * hd].view(B, S, nh, hd)
+        k = qkv[:, nh * hd:(nh + nkv) * hd].view(B, S, nkv, hd)
+        v = qkv[:, (nh + nkv) * hd:].view(B, S, nkv, hd)
+        ops.attn_bwd(q, k, v, attn, dattn.view(B, S, nh, hd), lse, causal=True, kmask=meta["kmask"],
+                     dq=dqkv[:, : nh * hd].view(B, S, nh, hd), dk=dqkv[:, nh * hd:(nh + nkv) * hd].view(B, S, nkv, hd),
+                     dv=dqkv[:, (nh + nkv) * hd:].view(B, S, nkv, hd))
+        ops.rope_(dqkv, meta["pos"], meta["cos"], meta["sin"], nh + nkv, hd, inverse=True)
+        h = ops.rmsnorm_fwd(x2, ln1, meta["eps"], meta["hf_cast"])
+        dh = ops.gemm(dqkv, qkv_w, b_mn=True)
+        g_qkv = wgrad(p_qkv, dqkv, h)
+        del dqkv, h
+        dx, dg1 = ops.rmsnorm_bwd(dh, x2, ln1, rstd1, dres=dx1)
+        g_ln1 = vgrad(p_ln1, dg1)
+        return None, dx.view(B, S, H), g_ln1, g_qkv, g_o, g_ln2, g_gu, g_down
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# embedding + image splice, lm_head + loss
+# ------------------------------------------------------------------------------------------------------------------
+class EmbedSpliceFn(torch.autograd.Function):
+    """cambrian_arch.py:413-420 + :457-490 (static branch): embed_tokens gather, image span replace, newline column."""
+
+    @staticmethod
+    def forward(ctx, meta, embed_w, img, newline):
+        ids, img_start, q_side = meta["ids"], meta["img_start"], meta["q_side"]
+        ctx.meta = meta
+        ctx.has_img = img is not None
+        ctx.vshape = embed_w.shape
+        return ops.embed_splice(ids, img_start, embed_w, img, newline, q_side)
+
+    @staticmethod
+    def backward(ctx, dout):
+        meta = ctx.meta
+        p_embed, p_newline = meta["params"]
+        dout = dout.contiguous()
+        d_embed_ret = None
+        tgt = None
+        if ctx.needs_input_grad[1]:
+            mg = getattr(p_embed, "main_grad", None)
+            if mg is not None:
+                fresh = getattr(p_embed, "_cb_fresh", None)
+                if fresh is not None and "all" not in fresh:
+                    mg.zero_()
+                    fresh.add("all")
+                tgt = mg
+            else:
+                tgt = torch.zeros(ctx.vshape, dtype=torch.bfloat16, device=dout.device)
+                d_embed_ret = tgt
+        d_img, d_nl_rows = ops.embed_splice_bwd(dout, meta["ids"], meta["img_start"], tgt, meta["q_side"], ctx.has_img)
+        d_nl = None
+        if ctx.has_img and ctx.needs_input_grad[3]:
+            d_nl = vgrad(p_newline, ops.group_colsum(d_nl_rows, 1).view(-1))
+        return None, d_embed_ret, d_img, d_nl
+
+
+class LMHeadLossFn(torch.autograd.Function):
+    """cambrian_llama.py:402-422: lm_head -> logits.float() -> shift -> CrossEntropyLoss(mean over non-ignored), computed
+    in row chunks so the [B*S, V] logits are never resident at once; the backward GEMMs run inside the forward (the
+    per-chunk (softmax - onehot) overwrites the chunk's logits), so the only saved tensor is dhidden."""
+
+    @staticmethod
+    def forward(ctx, meta, hidden, weight):
+        labels = meta["shift_labels"]  # int64 [B*S]: labels[b, s+1] at row (b, s), -100 on the last position
+        rows, H = hidden.reshape(-1, hidden.shape[-1]).shape
+        h2 = hidden.reshape(rows, H)
+        V = weight.shape[0]
+        dev = hidden.device
+        chunk = meta.get("chunk", 4096)
+        loss_rows = torch.empty(rows, dtype=torch.float32, device=dev)
+        acc = torch.zeros(2, dtype=torch.float32, device=dev)
+        n_valid = meta["n_valid"]  # python int (known on the host from the collator) — no device sync
+        train = meta["train"]
+        p_w = meta["params"][0]
+        dh = torch.empty_like(h2) if train else None
+        gscale = 1.0 / max(n_valid, 1)
+        logits = torch.empty((min(chunk, rows), V), dtype=torch.bfloat16, device=dev)
+        for r0 in range(0, rows, chunk):
+            r1 = min(rows, r0 + chunk)
+            lg = logits[: r1 - r0]
+            ops.gemm(h2[r0:r1], weight, out=lg)
+            ops.cross_entropy(lg, labels[r0:r1], loss_rows[r0:r1], acc, gscale, train)
+            if train:
+                ops.gemm(lg, weight, b_mn=True, out=dh[r0:r1])
+                wgrad(p_w, lg, h2[r0:r1])
+        ctx.train = train
+        ctx.hshape = hidden.shape
+        if train:
+            ctx.save_for_backward(dh)
+        loss = acc[0] * gscale
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dh,) = ctx.saved_tensors
+        # dloss is 1.0 for a plain loss.backward(); a scaled loss would need one more scaling kernel
+        return None, dh.view(ctx.hshape), None

@@ -33,16 +33,16 @@ int gemm_bf16(const void*, const void*, void*, int, int, int, int, long long, lo
               long long, long long, int, int, const void*, const void*, const void*, long long, long long, float,
               int, int, int, int, cudaStream_t);
 int sva_window_attn_fwd_launch(const void*, void*, float*, int, const void* const*, const void* const*,
-                               const void* const*, const int*, int, int, int, cudaStream_t);
+                               const void* const*, const int*, int, int, int, int, cudaStream_t);
 int sva_window_attn_bwd_launch(const void*, const void*, const void*, const float*, void*, int,
                                const void* const*, const void* const*, const void* const*, void* const*,
-                               void* const*, const int*, int, int, int, cudaStream_t);
+                               void* const*, const int*, int, int, int, int, cudaStream_t);
 int layernorm_fwd(const void*, const void*, const void*, void*, float*, float*, long long, int, float,
                   const void*, int, int, cudaStream_t);
-int layernorm_bwd(const void*, const void*, const void*, const float*, const float*, void*, void*, void*,
+int layernorm_bwd(const void*, const void*, const void*, const float*, const float*, void*, const void*, void*, void*,
                   float*, long long, long long, int, const void*, int, int, cudaStream_t);
 int rmsnorm_fwd(const void*, const void*, void*, float*, long long, int, float, int, cudaStream_t);
-int rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, void*, float*, long long,
+int rmsnorm_bwd(const void*, const void*, const void*, const float*, void*, const void*, void*, float*, long long,
                 long long, int, cudaStream_t);
 long long norm_bwd_workspace_floats(long long, int);
 
@@ -99,16 +99,16 @@ int cb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int
 
 int cb_sva_window_attn_fwd(const void* q, void* out, float* lse, int num_towers, const void* const* k,
                            const void* const* v, const void* const* mask, const int* r, int batch,
-                           int q_side, int hidden, void* stream) {
-  return cb::sva_window_attn_fwd_launch(q, out, lse, num_towers, k, v, mask, r, batch, q_side, hidden,
+                           int q_side, int hidden, int windowed, void* stream) {
+  return cb::sva_window_attn_fwd_launch(q, out, lse, num_towers, k, v, mask, r, batch, q_side, hidden, windowed,
                                         ST(stream));
 }
 int cb_sva_window_attn_bwd(const void* q, const void* out, const void* dout, const float* lse, void* dq,
                            int num_towers, const void* const* k, const void* const* v,
                            const void* const* mask, void* const* dk, void* const* dv, const int* r,
-                           int batch, int q_side, int hidden, void* stream) {
+                           int batch, int q_side, int hidden, int windowed, void* stream) {
   return cb::sva_window_attn_bwd_launch(q, out, dout, lse, dq, num_towers, k, v, mask, dk, dv, r, batch,
-                                        q_side, hidden, ST(stream));
+                                        q_side, hidden, windowed, ST(stream));
 }
 
 int cb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
@@ -116,9 +116,9 @@ int cb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y
   return cb::layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, C, eps, pos, side, r, ST(stream));
 }
 int cb_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                     void* dx, void* dgamma, void* dbeta, float* workspace, int64_t workspace_floats,
-                     int64_t rows, int C, const void* pos, int side, int r, void* stream) {
-  return cb::layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, workspace_floats, rows, C,
+                     void* dx, const void* dres, void* dgamma, void* dbeta, float* workspace,
+                     int64_t workspace_floats, int64_t rows, int C, const void* pos, int side, int r, void* stream) {
+  return cb::layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres, dgamma, dbeta, workspace, workspace_floats, rows, C,
                            pos, side, r, ST(stream));
 }
 int cb_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int64_t rows, int C, float eps,
@@ -126,9 +126,9 @@ int cb_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int64
   return cb::rmsnorm_fwd(x, gamma, y, rstd, rows, C, eps, hf_cast, ST(stream));
 }
 int cb_rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* rstd, void* dx,
-                   void* dgamma, float* workspace, int64_t workspace_floats, int64_t rows, int C,
+                   const void* dres, void* dgamma, float* workspace, int64_t workspace_floats, int64_t rows, int C,
                    void* stream) {
-  return cb::rmsnorm_bwd(dy, x, gamma, rstd, dx, dgamma, workspace, workspace_floats, rows, C, ST(stream));
+  return cb::rmsnorm_bwd(dy, x, gamma, rstd, dx, dres, dgamma, workspace, workspace_floats, rows, C, ST(stream));
 }
 int64_t cb_norm_bwd_workspace_floats(int64_t rows, int C) { return cb::norm_bwd_workspace_floats(rows, C); }
 

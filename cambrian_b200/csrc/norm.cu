@@ -38,6 +38,7 @@ struct PosAdd {
   int side, r;
 };
 __device__ __forceinline__ int pos_index(const PosAdd& p, long long row) {
+  if (p.side == 0) return (int)(row % ((long long)p.r * p.r));  // window-rearranged layout [N, r*r, C]
   const int cell = (int)(row % ((long long)p.side * p.side));
   const int y = cell / p.side, x = cell - y * p.side;
   return (y % p.r) * p.r + (x % p.r);
@@ -129,7 +130,8 @@ template <int TPR, bool RMS>
 __global__ void __launch_bounds__(TPR < 256 ? 256 : TPR)
 norm_bwd_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, const bf16* __restrict__ gamma,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dX,
-                float* __restrict__ part_g, float* __restrict__ part_b, long long rows, int C, PosAdd pa) {
+                const bf16* __restrict__ dRes, float* __restrict__ part_g, float* __restrict__ part_b, long long rows,
+                int C, PosAdd pa) {
   constexpr int RPB = TPR < 256 ? 256 / TPR : 1;
   __shared__ float red[RPB * (TPR / 32) + 1];
   const int slot = threadIdx.x / TPR, tir = threadIdx.x % TPR;
@@ -193,6 +195,12 @@ norm_bwd_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, const b
 #pragma unroll
           for (int e = 0; e < 8; ++e)
             o[e] = RMS ? rstd * (dy[i][e] - x[i][e] * s2) : rstd * (dy[i][e] - s1 - x[i][e] * s2);
+          if (dRes) {  // fused residual-stream gradient: dx = d_residual + d_norm_input
+            float t[8];
+            unpack8(ldg_nc(reinterpret_cast<const uint4*>(dRes + row * C) + vi), t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += t[e];
+          }
           dxp[vi] = pack8(o);
         }
       }
@@ -265,8 +273,8 @@ static int norm_fwd_t(const void* x, const void* gamma, const void* beta, void* 
 
 template <bool RMS>
 static int norm_bwd_t(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                      void* dx, void* dgamma, void* dbeta, float* workspace, long long ws_floats, long long rows,
-                      int C, PosAdd pa, cudaStream_t st) {
+                      void* dx, const void* dres, void* dgamma, void* dbeta, float* workspace, long long ws_floats,
+                      long long rows, int C, PosAdd pa, cudaStream_t st) {
   const int tpr = pick_tpr(C);
   CB_CHECK_ARG(C % 8 == 0 && tpr != 0, "norm bwd: C=%d must be a multiple of 8 and <= 16384", C);
   CB_CHECK_ARG(rows > 0, "norm bwd: rows=%lld", rows);
@@ -281,8 +289,8 @@ static int norm_bwd_t(const void* dy, const void* x, const void* gamma, const fl
   float* part_b = workspace + P * C;
 #define CB_NORM_BWD(T)                                                                                  \
   norm_bwd_kernel<T, RMS><<<(unsigned)grid, T < 256 ? 256 : T, 0, st>>>(                               \
-      (const bf16*)dy, (const bf16*)x, (const bf16*)gamma, mean, rstd, (bf16*)dx, part_g, part_b, rows, \
-      C, pa);
+      (const bf16*)dy, (const bf16*)x, (const bf16*)gamma, mean, rstd, (bf16*)dx, (const bf16*)dres, part_g, part_b, \
+      rows, C, pa);
   switch (tpr) {
     case 32: CB_NORM_BWD(32) break;
     case 64: CB_NORM_BWD(64) break;
@@ -300,24 +308,24 @@ static int norm_bwd_t(const void* dy, const void* x, const void* gamma, const fl
 
 int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
                   long long rows, int C, float eps, const void* pos, int side, int r, cudaStream_t st) {
-  PosAdd pa{(const bf16*)pos, side > 0 ? side : 1, r > 0 ? r : 1};
+  PosAdd pa{(const bf16*)pos, side >= 0 ? side : 0, r > 0 ? r : 1};
   return norm_fwd_t<false>(x, gamma, beta, y, mean, rstd, rows, C, eps, 0, pa, st);
 }
 int layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                  void* dx, void* dgamma, void* dbeta, float* ws, long long ws_floats, long long rows, int C,
-                  const void* pos, int side, int r, cudaStream_t st) {
-  PosAdd pa{(const bf16*)pos, side > 0 ? side : 1, r > 0 ? r : 1};
-  return norm_bwd_t<false>(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, ws, ws_floats, rows, C, pa, st);
+                  void* dx, const void* dres, void* dgamma, void* dbeta, float* ws, long long ws_floats, long long rows,
+                  int C, const void* pos, int side, int r, cudaStream_t st) {
+  PosAdd pa{(const bf16*)pos, side >= 0 ? side : 0, r > 0 ? r : 1};
+  return norm_bwd_t<false>(dy, x, gamma, mean, rstd, dx, dres, dgamma, dbeta, ws, ws_floats, rows, C, pa, st);
 }
 int rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, long long rows, int C, float eps,
                 int hf_cast, cudaStream_t st) {
   PosAdd pa{nullptr, 1, 1};
   return norm_fwd_t<true>(x, gamma, nullptr, y, nullptr, rstd, rows, C, eps, hf_cast, pa, st);
 }
-int rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* rstd, void* dx, void* dgamma,
-                float* ws, long long ws_floats, long long rows, int C, cudaStream_t st) {
+int rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* rstd, void* dx, const void* dres,
+                void* dgamma, float* ws, long long ws_floats, long long rows, int C, cudaStream_t st) {
   PosAdd pa{nullptr, 1, 1};
-  return norm_bwd_t<true>(dy, x, gamma, nullptr, rstd, dx, dgamma, nullptr, ws, ws_floats, rows, C, pa, st);
+  return norm_bwd_t<true>(dy, x, gamma, nullptr, rstd, dx, dres, dgamma, nullptr, ws, ws_floats, rows, C, pa, st);
 }
 long long norm_bwd_workspace_floats(long long rows, int C) {
   const int tpr = pick_tpr(C);

@@ -32,6 +32,7 @@ struct SvaArgs {
   int num_towers;
   int q_side;
   int n_queries;  // B * q_side * q_side
+  int windowed;   // 1: K/V are window-rearranged [N, r*r, C] (reference layout); 0: natural [B, side*side, C]
 };
 
 __device__ __forceinline__ float reduce8(float v) {
@@ -71,7 +72,7 @@ sva_window_attn_fwd(const bf16* __restrict__ Q, bf16* __restrict__ O, float* __r
     for (int w = 0; w < r * r; ++w) {
       if (mk && !mk[w]) continue;  // warp-uniform
       const int dy = w / r, dx = w - dy * r;
-      const size_t row = base + (size_t)(qy * r + dy) * side + (qx * r + dx);
+      const size_t row = a.windowed ? (size_t)n * r * r + w : base + (size_t)(qy * r + dy) * side + (qx * r + dx);
       const uint4* kp = reinterpret_cast<const uint4*>(a.k[t] + row * SVA_HIDDEN) + lane;
       const uint4* vp = reinterpret_cast<const uint4*>(a.v[t] + row * SVA_HIDDEN) + lane;
       uint4 kr[4], vr[4];
@@ -149,7 +150,7 @@ sva_window_attn_bwd(const bf16* __restrict__ Q, const bf16* __restrict__ O, cons
     const uint8_t* mk = a.mask[t] ? a.mask[t] + (size_t)n * r * r : nullptr;
     for (int w = 0; w < r * r; ++w) {
       const int dy = w / r, dx = w - dy * r;
-      const size_t row = base + (size_t)(qy * r + dy) * side + (qx * r + dx);
+      const size_t row = a.windowed ? (size_t)n * r * r + w : base + (size_t)(qy * r + dy) * side + (qx * r + dx);
       uint4* dkp = reinterpret_cast<uint4*>(a.dk[t] + row * SVA_HIDDEN) + lane;
       uint4* dvp = reinterpret_cast<uint4*>(a.dv[t] + row * SVA_HIDDEN) + lane;
       if (mk && !mk[w]) {  // masked key: no gradient, but the rows must still be defined
@@ -198,12 +199,13 @@ sva_window_attn_bwd(const bf16* __restrict__ Q, const bf16* __restrict__ O, cons
 }
 
 static int fill_args(SvaArgs& a, int num_towers, const void* const* k, const void* const* v,
-                     const void* const* mask, const int* r, int batch, int q_side) {
+                     const void* const* mask, const int* r, int batch, int q_side, int windowed) {
   CB_CHECK_ARG(num_towers >= 1 && num_towers <= SVA_MAX_TOWERS, "sva: num_towers=%d out of [1,%d]", num_towers,
                SVA_MAX_TOWERS);
   CB_CHECK_ARG(batch > 0 && q_side > 0, "sva: empty query grid");
   a.num_towers = num_towers;
   a.q_side = q_side;
+  a.windowed = windowed;
   a.n_queries = batch * q_side * q_side;
   for (int t = 0; t < num_towers; ++t) {
     CB_CHECK_ARG(r[t] >= 1, "sva: window side r[%d]=%d must be >= 1", t, r[t]);
@@ -220,10 +222,10 @@ static int fill_args(SvaArgs& a, int num_towers, const void* const* k, const voi
 
 int sva_window_attn_fwd_launch(const void* q, void* out, float* lse, int num_towers, const void* const* k,
                                const void* const* v, const void* const* mask, const int* r, int batch,
-                               int q_side, int hidden, cudaStream_t stream) {
+                               int q_side, int hidden, int windowed, cudaStream_t stream) {
   CB_CHECK_ARG(hidden == SVA_HIDDEN, "sva: hidden=%d unsupported (16 heads x 64 = 1024 only)", hidden);
   SvaArgs a;
-  int rc = fill_args(a, num_towers, k, v, mask, r, batch, q_side);
+  int rc = fill_args(a, num_towers, k, v, mask, r, batch, q_side, windowed);
   if (rc) return rc;
   const int grid = (a.n_queries + 3) / 4;
   sva_window_attn_fwd<<<grid, 128, 0, stream>>>(static_cast<const bf16*>(q), static_cast<bf16*>(out), lse, a);
@@ -234,11 +236,11 @@ int sva_window_attn_fwd_launch(const void* q, void* out, float* lse, int num_tow
 int sva_window_attn_bwd_launch(const void* q, const void* out, const void* dout, const float* lse, void* dq,
                                int num_towers, const void* const* k, const void* const* v,
                                const void* const* mask, void* const* dk, void* const* dv, const int* r,
-                               int batch, int q_side, int hidden, cudaStream_t stream) {
+                               int batch, int q_side, int hidden, int windowed, cudaStream_t stream) {
   CB_CHECK_ARG(hidden == SVA_HIDDEN, "sva: hidden=%d unsupported (16 heads x 64 = 1024 only)", hidden);
   CB_CHECK_ARG(lse != nullptr, "sva bwd: LSE from the forward pass is required");
   SvaArgs a;
-  int rc = fill_args(a, num_towers, k, v, mask, r, batch, q_side);
+  int rc = fill_args(a, num_towers, k, v, mask, r, batch, q_side, windowed);
   if (rc) return rc;
   for (int t = 0; t < num_towers; ++t) {
     CB_CHECK_ARG(dk[t] && dv[t], "sva bwd: null dK/dV for tower %d", t);

@@ -93,7 +93,7 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, **kw) -> torch.Tens
     return y.view(*lead, weight.shape[0])
 
 
-def sva_window_attn_fwd(q, ks, vs, masks, rs, batch: int, q_side: int, need_lse: bool = True):
+def sva_window_attn_fwd(q, ks, vs, masks, rs, batch: int, q_side: int, need_lse: bool = True, windowed: bool = False):
     _require_cuda_bf16(q, *ks, *vs)
     n, hidden = q.shape
     out = torch.empty_like(q)
@@ -104,12 +104,12 @@ def sva_window_attn_fwd(q, ks, vs, masks, rs, batch: int, q_side: int, need_lse:
                  for m in masks]
         mk = ptr_array(masks)
     rc = _lib.load().cb_sva_window_attn_fwd(ptr(q), ptr(out), ptr(lse), len(ks), ptr_array(ks), ptr_array(vs),
-                                            mk, int_array(rs), batch, q_side, hidden, stream())
+                                            mk, int_array(rs), batch, q_side, hidden, int(windowed), stream())
     check(rc, "cb_sva_window_attn_fwd")
     return out, lse
 
 
-def sva_window_attn_bwd(q, out, dout, lse, ks, vs, masks, rs, batch: int, q_side: int):
+def sva_window_attn_bwd(q, out, dout, lse, ks, vs, masks, rs, batch: int, q_side: int, windowed: bool = False):
     _require_cuda_bf16(q, out, dout, *ks, *vs)
     dq = torch.empty_like(q)
     dks = [torch.empty_like(k) for k in ks]
@@ -121,7 +121,7 @@ def sva_window_attn_bwd(q, out, dout, lse, ks, vs, masks, rs, batch: int, q_side
         mk = ptr_array(masks)
     rc = _lib.load().cb_sva_window_attn_bwd(ptr(q), ptr(out), ptr(dout), ptr(lse), ptr(dq), len(ks),
                                             ptr_array(ks), ptr_array(vs), mk, ptr_array(dks), ptr_array(dvs),
-                                            int_array(rs), batch, q_side, q.shape[1], stream())
+                                            int_array(rs), batch, q_side, q.shape[1], int(windowed), stream())
     check(rc, "cb_sva_window_attn_bwd")
     return dq, dks, dvs
 
@@ -143,7 +143,7 @@ def layernorm_fwd(x, gamma, beta, eps: float = 1e-5, pos=None, side: int = 0, r:
     return (y, mean, rstd) if save_stats else y
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, pos=None, side: int = 0, r: int = 0, has_beta: bool = True):
+def layernorm_bwd(dy, x, gamma, mean, rstd, pos=None, side: int = 0, r: int = 0, has_beta: bool = True, dres=None):
     _require_cuda_bf16(dy, x, gamma, pos)
     C_ = x.shape[-1]
     x2, dy2 = x.reshape(-1, C_), dy.reshape(-1, C_)
@@ -153,8 +153,9 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, pos=None, side: int = 0, r: int = 0,
     dbeta = torch.empty_like(gamma) if has_beta else None
     nws = _lib.load().cb_norm_bwd_workspace_floats(rows, C_)
     ws = workspace(nws, x.device)
-    rc = _lib.load().cb_layernorm_bwd(ptr(dy2), ptr(x2), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dgamma),
-                                      ptr(dbeta), ptr(ws), ws.numel(), rows, C_, ptr(pos), side, r, stream())
+    rc = _lib.load().cb_layernorm_bwd(ptr(dy2), ptr(x2), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dres),
+                                      ptr(dgamma), ptr(dbeta), ptr(ws), ws.numel(), rows, C_, ptr(pos), side, r,
+                                      stream())
     check(rc, "cb_layernorm_bwd")
     return dx.view(x.shape), dgamma, dbeta
 
@@ -173,7 +174,7 @@ def rmsnorm_fwd(x, gamma, eps: float = 1e-6, hf_cast: bool = False, save_stats=F
     return (y, rstd) if save_stats else y
 
 
-def rmsnorm_bwd(dy, x, gamma, rstd):
+def rmsnorm_bwd(dy, x, gamma, rstd, dres=None):
     _require_cuda_bf16(dy, x, gamma)
     C_ = x.shape[-1]
     x2, dy2 = x.reshape(-1, C_), dy.reshape(-1, C_)
@@ -182,7 +183,7 @@ def rmsnorm_bwd(dy, x, gamma, rstd):
     dgamma = torch.empty_like(gamma)
     nws = _lib.load().cb_norm_bwd_workspace_floats(rows, C_)
     ws = workspace(nws, x.device)
-    rc = _lib.load().cb_rmsnorm_bwd(ptr(dy2), ptr(x2), ptr(gamma), ptr(rstd), ptr(dx), ptr(dgamma), ptr(ws),
+    rc = _lib.load().cb_rmsnorm_bwd(ptr(dy2), ptr(x2), ptr(gamma), ptr(rstd), ptr(dx), ptr(dres), ptr(dgamma), ptr(ws),
                                     ws.numel(), rows, C_, stream())
     check(rc, "cb_rmsnorm_bwd")
     return dx.view(x.shape), dgamma

@@ -63,14 +63,16 @@ int cb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int
  *   q, out : [batch*q_side*q_side, hidden] bf16 (hidden = 1024 = 16 heads x 64)
  *   k[t], v[t] : [batch, (r[t]*q_side)^2, hidden] bf16 projected key/value grids in natural layout
  *   mask[t] : [batch*q_side*q_side, r[t]*r[t]] bool (1 byte) or NULL (= all true); `mask` itself may be NULL
- *   lse : [batch*q_side*q_side, 16] fp32 log2-domain log-sum-exp, needed by the backward (may be NULL) */
+ *   lse : [batch*q_side*q_side, 16] fp32 log2-domain log-sum-exp, needed by the backward (may be NULL)
+ *   windowed = 1: k/v are the reference's window-rearranged [N, r*r, hidden] tensors (vision_sampler.py API);
+ *   windowed = 0: natural grid layout (the fast path used by cambrian_arch: no permute/contiguous copies) */
 int cb_sva_window_attn_fwd(const void* q, void* out, float* lse, int num_towers, const void* const* k,
                            const void* const* v, const void* const* mask, const int* r, int batch,
-                           int q_side, int hidden, void* stream);
+                           int q_side, int hidden, int windowed, void* stream);
 int cb_sva_window_attn_bwd(const void* q, const void* out, const void* dout, const float* lse, void* dq,
                            int num_towers, const void* const* k, const void* const* v,
                            const void* const* mask, void* const* dk, void* const* dv, const int* r,
-                           int batch, int q_side, int hidden, void* stream);
+                           int batch, int q_side, int hidden, int windowed, void* stream);
 
 /* ---- normalisation ----------------------------------------------------------------------------
  * LayerNorm over the last dim C (nn.LayerNorm, eps in fp32 statistics).  `pos` (may be NULL) is the
@@ -79,15 +81,17 @@ int cb_sva_window_attn_bwd(const void* q, const void* out, const void* dout, con
  * mean/rstd [rows] fp32 are written when non-NULL (needed by the backward). */
 int cb_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd,
                      int64_t rows, int C, float eps, const void* pos, int side, int r, void* stream);
+/* dres (may be NULL): gradient arriving on the residual branch, fused as dx = dres + d(norm input).
+ * side = 0 selects the window-rearranged layout [N, r*r, C] for `pos` (row % (r*r)); side > 0 the natural grid. */
 int cb_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
-                     void* dx, void* dgamma, void* dbeta, float* workspace, int64_t workspace_floats,
-                     int64_t rows, int C, const void* pos, int side, int r, void* stream);
+                     void* dx, const void* dres, void* dgamma, void* dbeta, float* workspace,
+                     int64_t workspace_floats, int64_t rows, int C, const void* pos, int side, int r, void* stream);
 /* LLaMA RMSNorm.  hf_cast = 0: (w * x_hat_fp32).to(bf16) — the variant the reference trains with
  * (train_fsdp.py:1429-1435);  hf_cast = 1: w * x_hat.to(bf16) — stock HF LlamaRMSNorm (inference). */
 int cb_rmsnorm_fwd(const void* x, const void* gamma, void* y, float* rstd, int64_t rows, int C, float eps,
                    int hf_cast, void* stream);
 int cb_rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* rstd, void* dx,
-                   void* dgamma, float* workspace, int64_t workspace_floats, int64_t rows, int C,
+                   const void* dres, void* dgamma, float* workspace, int64_t workspace_floats, int64_t rows, int C,
                    void* stream);
 int64_t cb_norm_bwd_workspace_floats(int64_t rows, int C);
 

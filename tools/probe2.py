@@ -71,7 +71,7 @@ def attn_case(B, Sq, Skv, nh, nkv, hd, causal, use_mask, bwd, packed=False):
     torch.cuda.synchronize()
     errs = [rel_err(o, ref)]
     if bwd:
-        do = torch.randn_like(ref).bfloat16()
+        do = torch.randn(ref.shape, device=dev).bfloat16()
         ref.backward(do.float())
         dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, causal=causal, kmask=kmask)
         torch.cuda.synchronize()
@@ -294,6 +294,17 @@ def group_elem():
     x = torch.randn(8 * 2048, 14336 * 2, device=dev).bfloat16()
     ms = timeit(lambda: ops.swiglu_fwd(x[:, :14336], x[:, 14336:]))
     print(f"perf swiglu fwd: {ms * 1e3:.0f} us {3 * 16384 * 14336 * 2 / ms / 1e6:.0f} GB/s", flush=True)
+
+
+def group_attn_prof():
+    B, S, nh, nkv, hd = 1, 2048, 32, 8, 128
+    q = torch.randn(B, S, nh, hd, device=dev).bfloat16()
+    k = torch.randn(B, S, nkv, hd, device=dev).bfloat16()
+    v = torch.randn(B, S, nkv, hd, device=dev).bfloat16()
+    for _ in range(2):
+        o, lse = ops.attn_fwd(q, k, v, causal=True, need_lse=True)
+        ops.attn_bwd(q, k, v, o, o, lse, causal=True)
+    torch.cuda.synchronize()
 
 
 if __name__ == "__main__":
