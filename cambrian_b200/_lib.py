@@ -53,6 +53,8 @@ SIGNATURES = {
     "cb_f32_to_bf16": (_i, [_vp, _vp, _i64, _i, _i64, _f, _vp]),
     "cb_cross_entropy": (_i, [_vp] * 4 + [_i64, _i64, _i64, _f, _i, _i64, _vp]),
     "cb_adamw": (_i, [_vp] * 5 + [_i64] + [_f] * 5 + [_i, _f, _vp]),
+    "cb_span_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "cb_span_scatter": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

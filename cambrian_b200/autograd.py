@@ -312,8 +312,11 @@ class DecoderLayerFn(torch.autograd.Function):
         return out.view(B, S, H), None
 
     @staticmethod
-    def forward(ctx, meta, x, ln1, qkv_w, o_w, ln2, gu_w, down_w):
+    def forward(ctx, meta, x, ln1, q_w, k_w, v_w, o_w, ln2, gate_w, up_w, down_w):
+        # q_w/k_w/v_w and gate_w/up_w are the HF-named leaf parameters (for autograd bookkeeping); the GEMMs use the
+        # fused views meta["qkv_w"] / meta["gu_w"] over the same storage (CBLlamaDecoderLayer._fused()).
         keep = not meta["recompute"]
+        qkv_w, gu_w = meta["qkv_w"], meta["gu_w"]
         out, saved = DecoderLayerFn._forward(meta, x, ln1, qkv_w, o_w, ln2, gu_w, down_w, keep)
         ctx.meta = meta
         if keep:
@@ -332,6 +335,7 @@ class DecoderLayerFn(torch.autograd.Function):
         else:
             saved = sv[7:]
         rstd1, qkv, attn, lse, x1, rstd2, gu = saved
+        # p_qkv / p_gu: holders exposing .main_grad (fused view over the three / two adjacent grad slices) or None
         p_ln1, p_qkv, p_o, p_ln2, p_gu, p_down = meta["params"]
         B, S, H = x.shape
         nh, nkv, hd = meta["nh"], meta["nkv"], meta["hd"]
@@ -371,7 +375,12 @@ class DecoderLayerFn(torch.autograd.Function):
         del dqkv, h
         dx, dg1 = ops.rmsnorm_bwd(dh, x2, ln1, rstd1, dres=dx1)
         g_ln1 = vgrad(p_ln1, dg1)
-        return None, dx.view(B, S, H), g_ln1, g_qkv, g_o, g_ln2, g_gu, g_down
+        gq = gk = gv = gg = gup = None
+        if g_qkv is not None:  # no main_grad buffers: hand autograd the per-parameter slices of the fused gradient
+            gq, gk, gv = g_qkv[: nh * hd], g_qkv[nh * hd:(nh + nkv) * hd], g_qkv[(nh + nkv) * hd:]
+        if g_gu is not None:
+            gg, gup = g_gu[:I], g_gu[I:]
+        return None, dx.view(B, S, H), g_ln1, gq, gk, gv, g_o, g_ln2, gg, gup, g_down
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -434,6 +443,9 @@ class LMHeadLossFn(torch.autograd.Function):
         dh = torch.empty_like(h2) if train else None
         gscale = 1.0 / max(n_valid, 1)
         logits = torch.empty((min(chunk, rows), V), dtype=torch.bfloat16, device=dev)
+        dw_local = None
+        if train and getattr(p_w, "main_grad", None) is None:
+            dw_local = torch.empty_like(weight)
         for r0 in range(0, rows, chunk):
             r1 = min(rows, r0 + chunk)
             lg = logits[: r1 - r0]
@@ -441,16 +453,73 @@ class LMHeadLossFn(torch.autograd.Function):
             ops.cross_entropy(lg, labels[r0:r1], loss_rows[r0:r1], acc, gscale, train)
             if train:
                 ops.gemm(lg, weight, b_mn=True, out=dh[r0:r1])
-                wgrad(p_w, lg, h2[r0:r1])
+                if dw_local is None:
+                    wgrad(p_w, lg, h2[r0:r1])
+                else:
+                    ops.gemm(lg, h2[r0:r1], a_mn=True, b_mn=True, out=dw_local, accumulate=r0 > 0)
         ctx.train = train
         ctx.hshape = hidden.shape
+        ctx.has_dw = dw_local is not None
         if train:
-            ctx.save_for_backward(dh)
+            ctx.save_for_backward(dh, *([dw_local] if dw_local is not None else []))
         loss = acc[0] * gscale
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        (dh,) = ctx.saved_tensors
         # dloss is 1.0 for a plain loss.backward(); a scaled loss would need one more scaling kernel
-        return None, dh.view(ctx.hshape), None
+        dh = ctx.saved_tensors[0]
+        dw = ctx.saved_tensors[1] if ctx.has_dw else None
+        return None, dh.view(ctx.hshape), dw
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# in-LLM SVA site plumbing (cambrian_llama.py:168-207, static branch) and row broadcast
+# ------------------------------------------------------------------------------------------------------------------
+class SpanSplitFn(torch.autograd.Function):
+    """hidden [B,S,H] -> (latent queries [B*q*q, H] copied out of the image span, hidden passed through).
+
+    The pass-through output shares storage with `hidden`; SpanMergeFn later overwrites the latent rows in place, exactly
+    like the reference's `hidden_states[:, start:start+600] = ...` assignment.  Backward needs no add: the gradient of
+    the overwritten rows is replaced by the gradient that arrived through the latent-query branch."""
+
+    @staticmethod
+    def forward(ctx, hidden, start, q_side):
+        ctx.start, ctx.q_side = start, q_side
+        lat = ops.span_gather(hidden, start, q_side)
+        return lat, hidden.detach()
+
+    @staticmethod
+    def backward(ctx, d_lat, d_pass):
+        d_hidden = d_pass if d_pass.is_contiguous() else d_pass.contiguous()
+        ops.span_scatter_(d_hidden, d_lat.contiguous(), ctx.start, ctx.q_side)
+        return d_hidden, None, None
+
+
+class SpanMergeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, passthru, lat_new, start, q_side):
+        ctx.start, ctx.q_side = start, q_side
+        ops.span_scatter_(passthru, lat_new.contiguous(), start, q_side)
+        ctx.mark_dirty(passthru)
+        return passthru
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        return dout, ops.span_gather(dout, ctx.start, ctx.q_side), None, None
+
+
+class ExpandRowsFn(torch.autograd.Function):
+    """x [G, C] -> [G*rows, C] (each row repeated `rows` times): the `.expand(...).flatten(0,1)` of the global context
+    and of vision_query (cambrian_arch.py:383-385)."""
+
+    @staticmethod
+    def forward(ctx, x, rows):
+        ctx.rows = rows
+        return ops.group_broadcast(x.contiguous(), rows, 1.0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        G = dy.shape[0] // ctx.rows
+        return ops.group_colsum(dy.contiguous(), G, 1.0), None

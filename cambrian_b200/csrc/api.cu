@@ -78,6 +78,8 @@ int cross_entropy_launch(void*, const long long*, float*, float*, long long, lon
                          long long, cudaStream_t);
 int adamw_launch(float*, float*, float*, const void*, void*, long long, float, float, float, float, float, int, float,
                  cudaStream_t);
+int span_gather_launch(const void*, void*, int, int, int, int, int, cudaStream_t);
+int span_scatter_launch(void*, const void*, int, int, int, int, int, cudaStream_t);
 
 }  // namespace cb
 
@@ -214,6 +216,12 @@ int cb_cross_entropy(void* logits, const int64_t* labels, float* loss_rows, floa
                      int64_t ld, float grad_scale, int write_grad, int64_t ignore_index, void* stream) {
   return cb::cross_entropy_launch(logits, reinterpret_cast<const long long*>(labels), loss_rows, loss_acc, rows, V, ld,
                                   grad_scale, write_grad, ignore_index, ST(stream));
+}
+int cb_span_gather(const void* hidden, void* lat, int B, int S, int H, int start, int q_side, void* stream) {
+  return cb::span_gather_launch(hidden, lat, B, S, H, start, q_side, ST(stream));
+}
+int cb_span_scatter(void* hidden, const void* lat, int B, int S, int H, int start, int q_side, void* stream) {
+  return cb::span_scatter_launch(hidden, lat, B, S, H, start, q_side, ST(stream));
 }
 int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int step, float grad_scale, void* stream) {

@@ -185,35 +185,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     float m_ref = 0.f, l = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full(j & 1), (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tS = tS0 + (j & 1) * 128 + lane_off;
       const int k0 = j * 128;
       int kmax = p.Skv - k0;                                // keys beyond Skv
       if (p.causal) kmax = min(kmax, qi + coff - k0 + 1);   // keys beyond the diagonal
-      const uint8_t* km = p.kmask ? p.kmask + (size_t)b * p.Skv + k0 : nullptr;
-      // pass 1: row max
-      float tmax = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + c * 32, r);
-        tmem_ld_wait();
+      // key-padding mask of this tile as 4 x 32 bits, built cooperatively (lane l owns keys 4l..4l+3)
+      uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+      if (p.kmask) {
+        const uint8_t* km = p.kmask + (size_t)b * p.Skv + k0;
+        uint32_t nib = 0;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int kc = c * 32 + e;
-          const bool ok = kc < kmax && (!km || km[kc]);
-          if (ok) tmax = fmaxf(tmax, __uint_as_float(r[e]));
+        for (int e = 0; e < 4; ++e) {
+          const int kc = lane * 4 + e;
+          if (k0 + kc < p.Skv && km[kc]) nib |= 1u << e;
+        }
+        uint32_t v = nib << (4 * (lane & 7));
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        v |= __shfl_xor_sync(0xffffffffu, v, 4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mw[c] = __shfl_sync(0xffffffffu, v, 8 * c);
+      }
+      mbar_wait(s_full(j & 1), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tS = tS0 + (j & 1) * 128 + lane_off;
+      // one TMEM read of the whole 128-key row into registers
+      uint32_t sr[128];
+      tmem_ld32(tS, sr);
+      tmem_ld32(tS + 32, sr + 32);
+      tmem_ld32(tS + 64, sr + 64);
+      tmem_ld32(tS + 96, sr + 96);
+      tmem_ld_wait();
+      if (kmax < 128 || p.kmask) {  // branch-free masking: masked scores become -inf
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int rem = kmax - c * 32;
+          uint32_t bits = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+          bits &= mw[c];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sr[c * 32 + e] = ((bits >> e) & 1u) ? sr[c * 32 + e] : 0xff800000u;
         }
       }
-      tmax *= p.scale_log2;  // scale > 0 keeps the ordering; -inf stays -inf
+      float t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 128; e += 4) {
+        t0 = fmaxf(t0, __uint_as_float(sr[e]));
+        t1 = fmaxf(t1, __uint_as_float(sr[e + 1]));
+        t2 = fmaxf(t2, __uint_as_float(sr[e + 2]));
+        t3 = fmaxf(t3, __uint_as_float(sr[e + 3]));
+      }
+      float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * p.scale_log2;  // scale > 0 keeps ordering; -inf stays
       // lazy rescale (log2 domain): only move the reference max when it grows by > 8 (p <= 256)
       const bool grow = (j == 0) ? true : (tmax > m_ref + 8.f);
       if (__any_sync(0xffffffffu, grow)) {
         float m_new = (j == 0) ? tmax : fmaxf(m_ref, tmax);
         if (m_new == -INFINITY) m_new = 0.f;
         if (j > 0) {
-          const float corr = exp2f(m_ref - m_new);
+          const float corr = fast_exp2(m_ref - m_new);
           l *= corr;
           mbar_wait(pv_done, (j - 1) & 1);  // O accumulation of tile j-1 retired
           tc_fence_after();
@@ -232,30 +259,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       } else if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);  // P smem tile free again
       }
-      // pass 2: p = exp2(s*scale - m_ref), row sum, bf16 P tile in the K-major SWIZZLE_128B layout
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
+      // p = exp2(s*scale - m_ref) (masked: exp2(-inf) = 0), row sum, bf16 P tile in the K-major SWIZZLE_128B layout
+      const float neg_m = -m_ref;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int kc = c * 32 + e;
-          const bool ok = kc < kmax && (!km || km[kc]);
-          const float x = ok ? exp2f(__uint_as_float(r[e]) * p.scale_log2 - m_ref) : 0.f;
-          pv[e] = x;
-          l += x;
-        }
+      for (int g = 0; g < 16; ++g) {  // 16-byte chunk index along the 128 keys
+        float pv[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int g = c * 4 + u;  // 16-byte chunk index along the 128 keys
-          const uint32_t addr = sP + (g >> 3) * 16384 + row * 128 + (((g & 7) ^ (row & 7)) << 4);
-          const uint4 val = pack8(pv + u * 8);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(val.x), "r"(val.y), "r"(val.z),
-                       "r"(val.w) : "memory");
-        }
+        for (int e = 0; e < 8; ++e) pv[e] = fast_exp2(fmaf(__uint_as_float(sr[g * 8 + e]), p.scale_log2, neg_m));
+        l0 += pv[0] + pv[4];
+        l1 += pv[1] + pv[5];
+        l2 += pv[2] + pv[6];
+        l3 += pv[3] + pv[7];
+        const uint32_t addr = sP + (g >> 3) * 16384 + row * 128 + (((g & 7) ^ (row & 7)) << 4);
+        const uint4 val = pack8(pv);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(val.x), "r"(val.y), "r"(val.z),
+                     "r"(val.w) : "memory");
       }
+      l += (l0 + l1) + (l2 + l3);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
@@ -509,12 +530,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32(tA + lane_off + c * 32, rs);
         tmem_ld32(tB + lane_off + c * 32, rd);
         tmem_ld_wait();
+        // branch-free visibility mask for the 32 queries of this chunk
+        const int lo = max(qmin - c * 32, 0), hi = min(qmax - c * 32, 32);
+        uint32_t bits = 0u;
+        if (key_ok && hi > lo) bits = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
         float pv[32], ds[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int qc = c * 32 + e;
-          const bool ok = key_ok && qc >= qmin && qc < qmax;
-          const float pe = ok ? exp2f(__uint_as_float(rs[e]) * p.scale_log2 - stat[qc]) : 0.f;
+          float pe = fast_exp2(fmaf(__uint_as_float(rs[e]), p.scale_log2, -stat[qc]));
+          pe = ((bits >> e) & 1u) ? pe : 0.f;
           pv[e] = pe;
           ds[e] = pe * (__uint_as_float(rd[e]) - stat[128 + qc]);
         }

@@ -67,6 +67,12 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 __device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// single MUFU.EX2 (2^-inf = +0, no denormal range fix-up branches): softmax inner loops
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // 8 x bf16 <-> 8 x float through one 16-byte register quad
 struct alignas(16) bf16x8 {

@@ -449,6 +449,41 @@ __global__ void f32_to_bf16_kernel(const float4* __restrict__ in, bf16* __restri
   }
 }
 
+// ------------------------------------------------------------------- in-LLM SVA latent gather / scatter
+// cambrian_llama.py:168-207 (static branch): the q*(q+1) image positions [start, start + q*(q+1)) of the residual
+// stream hold q rows of (q latent queries + 1 newline token).  gather copies the q*q latent rows into a dense
+// [B*q*q, H] buffer; scatter writes (updated) latent rows back in place.  Newline rows are never touched.
+__global__ void span_gather_kernel(const bf16* __restrict__ hidden, bf16* __restrict__ lat, int B, int S, int H, int start,
+                                   int q_side) {
+  const int vpr = H >> 3;
+  const long long total = (long long)B * q_side * q_side * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpr);
+    long long t = i / vpr;
+    const int col = (int)(t % q_side);
+    t /= q_side;
+    const int row = (int)(t % q_side);
+    const int b = (int)(t / q_side);
+    const long long src = ((long long)b * S + start + row * (q_side + 1) + col) * H;
+    reinterpret_cast<uint4*>(lat)[i] = ldg_nc(reinterpret_cast<const uint4*>(hidden + src) + v);
+  }
+}
+__global__ void span_scatter_kernel(bf16* __restrict__ hidden, const bf16* __restrict__ lat, int B, int S, int H, int start,
+                                    int q_side) {
+  const int vpr = H >> 3;
+  const long long total = (long long)B * q_side * q_side * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpr);
+    long long t = i / vpr;
+    const int col = (int)(t % q_side);
+    t /= q_side;
+    const int row = (int)(t % q_side);
+    const int b = (int)(t / q_side);
+    const long long dst = ((long long)b * S + start + row * (q_side + 1) + col) * H;
+    reinterpret_cast<uint4*>(hidden + dst)[v] = ldg_nc(reinterpret_cast<const uint4*>(lat) + i);
+  }
+}
+
 // -------------------------------------------------------------------------------- cross entropy
 // One block per row of bf16 logits [rows, V]: loss_row = logsumexp(fp32(logits)) - logit[label]; rows with
 // label == ignore_index contribute 0.  If dlogits != null the row is overwritten IN PLACE with
@@ -660,7 +695,7 @@ int patchify_nchw_launch(const void* img, void* out, int B, int Cin, int R, int 
 }
 int patchify_nhwc_launch(const void* in, void* out, int B, int H, int W, int C, int p, cudaStream_t st) {
   VEC_CHECK(C, "patchify_nhwc");
-  CB_CHECK_ARG(H % p == 0 && W % p == 0, "patchify_nhwc: H, W must be multiples of p");
+  CB_CHECK_ARG(H >= p && W >= p, "patchify_nhwc: feature map smaller than the patch");  // remainder rows/cols are dropped (conv stride semantics)
   patchify_nhwc_kernel<<<grid_for((long long)B * H * W * (C / 8), 256), 256, 0, st>>>((const bf16*)in, (bf16*)out, B, H, W,
                                                                                      C, p);
   CB_CUDA_LAUNCH_CHECK("patchify_nhwc");
@@ -712,6 +747,24 @@ int f32_to_bf16_launch(const float* in, void* out, long long rows, int cols, lon
   if (n == 0) return CB_OK;
   f32_to_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>((const float4*)in, (bf16*)out, n / 8, cols / 8, out_ld, scale);
   CB_CUDA_LAUNCH_CHECK("f32_to_bf16");
+  return CB_OK;
+}
+int span_gather_launch(const void* hidden, void* lat, int B, int S, int H, int start, int q_side, cudaStream_t st) {
+  VEC_CHECK(H, "span_gather");
+  CB_CHECK_ARG(start >= 0 && start + q_side * (q_side + 1) <= S, "span_gather: image span [%d, +%d) outside sequence %d",
+               start, q_side * (q_side + 1), S);
+  span_gather_kernel<<<grid_for((long long)B * q_side * q_side * (H / 8), 256), 256, 0, st>>>((const bf16*)hidden, (bf16*)lat,
+                                                                                            B, S, H, start, q_side);
+  CB_CUDA_LAUNCH_CHECK("span_gather");
+  return CB_OK;
+}
+int span_scatter_launch(void* hidden, const void* lat, int B, int S, int H, int start, int q_side, cudaStream_t st) {
+  VEC_CHECK(H, "span_scatter");
+  CB_CHECK_ARG(start >= 0 && start + q_side * (q_side + 1) <= S, "span_scatter: image span [%d, +%d) outside sequence %d",
+               start, q_side * (q_side + 1), S);
+  span_scatter_kernel<<<grid_for((long long)B * q_side * q_side * (H / 8), 256), 256, 0, st>>>((bf16*)hidden, (const bf16*)lat,
+                                                                                             B, S, H, start, q_side);
+  CB_CUDA_LAUNCH_CHECK("span_scatter");
   return CB_OK;
 }
 int cross_entropy_launch(void* logits, const long long* labels, float* loss_rows, float* loss_acc, long long rows,

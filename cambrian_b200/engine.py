@@ -1,0 +1,120 @@
+"""Data-parallel training engine for the Cambrian hot path.
+
+One process per GPU.  All trainable parameters live in ONE flat bf16 buffer (the compute copy) with matching flat
+buffers for bf16 gradients, fp32 master weights and fp32 Adam moments:
+
+  * weight-gradient GEMMs accumulate straight into `param.main_grad` (a view of the flat gradient buffer), so
+    autograd never materialises or sums parameter gradients;
+  * gradient reduction = NCCL all-reduce over contiguous buckets of the flat gradient buffer, launched as soon as the
+    last parameter of a bucket has its gradient written (backward runs last-layer-first, buckets are laid out in the
+    same order), overlapping NVLink traffic with the remaining backward GEMMs; frozen towers are never reduced;
+  * the optimizer is one fused AdamW kernel over the flat buffers (fp32 master update -> bf16 compute copy).
+
+The reference does its gradient reduction inside torch_xla FSDP (`xm.all_reduce` helper at
+cambrian_trainer.py:181-190) and steps HF Trainer's AdamW (cambrian_trainer.py:242-381).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def _round8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class TrainEngine:
+    def __init__(self, model: torch.nn.Module, lr: float = 4e-5, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, bucket_mb: float = 256.0, process_group=None):
+        self.model = model
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.step_count = 0
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        if not named:
+            raise ValueError("TrainEngine: model has no trainable parameters")
+        dev = named[0][1].device
+        self.params = [p for _, p in named]
+        self.names = [n for n, _ in named]
+        offs, total = [], 0
+        for p in self.params:
+            if p.dtype != torch.bfloat16:
+                raise ValueError("TrainEngine expects bf16 parameters (fp32 masters are kept by the engine)")
+            offs.append(total)
+            total += _round8(p.numel())
+        self.offsets, self.total = offs, total
+        self.flat_p = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+        for p, o in zip(self.params, offs):
+            n = p.numel()
+            self.flat_p[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[o:o + n].view(p.shape)          # re-point: compute copy now lives in the flat buffer
+            p.main_grad = self.flat_g[o:o + n].view(p.shape)
+            p._cb_fresh = set()
+            p._cb_engine = self
+            p.grad = None
+        self.master = self.flat_p.float()
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        # buckets: contiguous parameter ranges of ~bucket_mb, reduced in reverse order during backward
+        self.buckets = []  # (start_elem, end_elem, [param indices])
+        cur, cur_start = [], 0
+        limit = int(bucket_mb * 1024 * 1024 / 2)
+        for i, (p, o) in enumerate(zip(self.params, offs)):
+            cur.append(i)
+            end = o + _round8(p.numel())
+            if end - cur_start >= limit:
+                self.buckets.append((cur_start, end, cur))
+                cur, cur_start = [], end
+        if cur:
+            self.buckets.append((cur_start, total, cur))
+        self._bucket_of = {}
+        for b, (_, _, idx) in enumerate(self.buckets):
+            for i in idx:
+                self._bucket_of[i] = b
+        self._pending = []
+        self._handles = []
+
+    # ---- per-step protocol ---------------------------------------------------------------------------------------
+    def zero_grad(self):
+        for p in self.params:
+            p._cb_fresh.clear()
+            p.grad = None
+        self._handles = []
+
+    def _finalize_unwritten(self):
+        """Parameters that received no gradient this step (unused modules) must not feed stale values to Adam."""
+        for p in self.params:
+            if not p._cb_fresh:
+                p.main_grad.zero_()
+
+    def reduce_gradients(self):
+        """Bucketed all-reduce (sum) of the flat gradient buffer; the 1/world average is folded into AdamW."""
+        if self.world == 1:
+            return
+        for (s, e, _) in reversed(self.buckets):
+            self._handles.append(dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+
+    def step(self):
+        self._finalize_unwritten()
+        self.reduce_gradients()
+        self.step_count += 1
+        ops.adamw(self.master, self.exp_avg, self.exp_avg_sq, self.flat_g, self.flat_p, self.lr, self.betas[0],
+                  self.betas[1], self.eps, self.wd, self.step_count, grad_scale=1.0 / self.world)
+
+    # ---- convenience ---------------------------------------------------------------------------------------------
+    def train_step(self, **batch):
+        self.zero_grad()
+        out = self.model(**batch)
+        out.loss.backward()
+        self.step()
+        return out.loss
+
+    def state_bytes(self):
+        return self.total * (2 + 2 + 4 + 4 + 4)

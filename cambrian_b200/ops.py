@@ -420,3 +420,16 @@ def cross_entropy(logits, labels, loss_rows, loss_acc, grad_scale: float, write_
 def adamw(p32, m, v, g16, p16, lr, beta1, beta2, eps, wd, step: int, grad_scale: float = 1.0):
     check(_lib.load().cb_adamw(ptr(p32), ptr(m), ptr(v), ptr(g16), ptr(p16), p32.numel(), float(lr), float(beta1),
                                float(beta2), float(eps), float(wd), int(step), float(grad_scale), stream()), "cb_adamw")
+
+
+def span_gather(hidden, start: int, q_side: int):
+    B, S, H = hidden.shape
+    lat = torch.empty((B * q_side * q_side, H), dtype=torch.bfloat16, device=hidden.device)
+    check(_lib.load().cb_span_gather(ptr(hidden), ptr(lat), B, S, H, start, q_side, stream()), "cb_span_gather")
+    return lat
+
+
+def span_scatter_(hidden, lat, start: int, q_side: int):
+    B, S, H = hidden.shape
+    check(_lib.load().cb_span_scatter(ptr(hidden), ptr(lat), B, S, H, start, q_side, stream()), "cb_span_scatter")
+    return hidden

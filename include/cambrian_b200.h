@@ -160,6 +160,10 @@ int cb_f32_to_bf16(const float* in, void* out, int64_t rows, int cols, int64_t o
  * with (softmax - onehot) * grad_scale. */
 int cb_cross_entropy(void* logits, const int64_t* labels, float* loss_rows, float* loss_acc, int64_t rows, int64_t V,
                      int64_t ld, float grad_scale, int write_grad, int64_t ignore_index, void* stream);
+/* in-LLM SVA site (cambrian_llama.py:168-207): gather the q*q latent rows of the image span [start, start+q*(q+1))
+ * of hidden [B,S,H] into lat [B*q*q, H] / scatter updated rows back in place (newline rows untouched) */
+int cb_span_gather(const void* hidden, void* lat, int B, int S, int H, int start, int q_side, void* stream);
+int cb_span_scatter(void* hidden, const void* lat, int B, int S, int H, int start, int q_side, void* stream);
 /* AdamW on fp32 master weights / moments with bf16 gradients, writing the bf16 compute copy */
 int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int step, float grad_scale, void* stream);

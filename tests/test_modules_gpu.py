@@ -1,0 +1,328 @@
+"""GPU parity tests of the drop-in modules against the CPU oracle (oracle/cambrian_oracle.py) on identical weights and
+seeded inputs: SVA sampler (both layouts, fwd + bwd), the four towers, the LLaMA decoder layer (fwd + bwd), and the full
+tiny Cambrian model (loss + parameter gradients + greedy generate token ids)."""
+import pytest
+import torch
+
+from helpers import (BF16_TOL, assert_close_bf16, ns, oracle_cfg, rel_err, sd_cpu32, tiny_cambrian_config,
+                     tower_image_sizes)
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def _cuda_bf16(m):
+    return m.to(device=dev, dtype=torch.bfloat16)
+
+
+@pytest.mark.parametrize("rs,use_mask", [([1, 1, 1, 1], False), ([1, 1, 1, 2], True), ([2, 1, 3], True)])
+def test_sva_sampler_matches_oracle(rs, use_mask):
+    from cambrian_b200.model.vision_sampler import VisionTokenSampler
+    from oracle import cambrian_oracle as O
+    torch.manual_seed(0)
+    B, q, D, depth = 2, 4, 256, 2
+    T = len(rs)
+    m = _cuda_bf16(VisionTokenSampler(D, 1024, [1024] * T, rs, 1024, depth))
+    for layer in m.layers:  # give pos_embed a realistic scale
+        for i, r in enumerate(rs):
+            if r > 1:
+                getattr(layer, f"pos_embed_{i}").data.mul_(0.1)
+    sd = sd_cpu32(m)
+    n = B * q * q
+    feats = [torch.randn(B, (r * q) ** 2, 1024) for r in rs]
+    queries = torch.randn(n, 1, D)
+    ctx = torch.randn(B, 1, 1024).expand(B, q * q, 1024).reshape(n, 1, 1024)
+    masks = None
+    if use_mask:
+        masks = []
+        for r in rs:
+            mk = torch.rand(n, r * r) > 0.3
+            mk[mk.sum(1) == 0] = True
+            masks.append(mk)
+    bf = lambda t: t.bfloat16().float()
+    # ---- oracle (fp32, CPU, autograd)
+    qo = bf(queries).requires_grad_()
+    fo = [bf(f).requires_grad_() for f in feats]
+    ref = O.sva_sampler(sd, "", qo, bf(ctx), [O.window_rearrange(f, q) for f in fo], masks, depth)
+    dout = torch.randn_like(ref)
+    ref.backward(bf(dout))
+    # ---- CUDA, natural layout (fast path)
+    qg = queries.to(dev).bfloat16().requires_grad_()
+    fg = [f.to(dev).bfloat16().requires_grad_() for f in feats]
+    mg = [None] * T if masks is None else [mk.to(dev) for mk in masks]
+    out = m(qg, ctx.to(dev).bfloat16(), *fg, *mg, natural_layout=(B, q))
+    out.backward(dout.to(dev).bfloat16())
+    assert_close_bf16(out, ref, "sva forward (natural)")
+    assert_close_bf16(qg.grad, qo.grad, "sva dqueries")
+    for i in range(T):
+        assert_close_bf16(fg[i].grad, fo[i].grad, f"sva dfeats[{i}]")
+    gref = torch.autograd.grad(O.sva_sampler({k: v.requires_grad_() for k, v in sd.items()}, "", bf(queries), bf(ctx),
+                                             [O.window_rearrange(bf(f), q) for f in feats], masks, depth),
+                               [sd[k] for k in sd], bf(dout))
+    for (k, p), g in zip(m.named_parameters(), gref):
+        assert_close_bf16(p.grad, g, f"sva grad {k}", tol=4e-2, cos=0.995)
+    # ---- CUDA, reference call convention (window-rearranged latents): same numbers
+    m.zero_grad()
+    fw = [O.window_rearrange(bf(f), q).to(dev).bfloat16() for f in feats]
+    out_w = m(queries.to(dev).bfloat16(), ctx.to(dev).bfloat16(), *fw, *mg)
+    assert_close_bf16(out_w, ref, "sva forward (window-rearranged API)")
+    assert rel_err(out_w, out) < 1e-2
+
+
+def test_sva_mask_shape_error():
+    from cambrian_b200.model.vision_sampler import VisionTokenSampler
+    m = _cuda_bf16(VisionTokenSampler(256, 1024, [1024], [1], 1024, 1))
+    q = torch.zeros(16, 1, 256, device=dev, dtype=torch.bfloat16)
+    c = torch.zeros(16, 1, 1024, device=dev, dtype=torch.bfloat16)
+    f = torch.zeros(16, 1, 1024, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        m(q, c, f, torch.ones(16, 3, dtype=torch.bool, device=dev))
+
+
+def _tower_pair(kind):
+    from cambrian_b200.model.multimodal_encoder.builder import build_vision_tower_aux_list
+    from oracle import cambrian_oracle as O
+    cfg = tiny_cambrian_config()
+    cfg.dino_config_overrides = dict(hidden_size=384, num_hidden_layers=2, num_attention_heads=6, mlp_ratio=4)
+    idx = {"siglip": 0, "clip": 1, "dino": 2, "convnext": 3}[kind]
+    args = ns(**{k: getattr(cfg, k) for k in ("siglip_config_overrides", "clip_config_overrides",
+                                               "convnext_config_overrides", "dino_config_overrides")},
+              mm_vision_tower_aux_list=[cfg.mm_vision_tower_aux_list[idx]],
+              mm_vision_tower_aux_token_len_list=[576 if kind != "convnext" else 64])
+    tower = build_vision_tower_aux_list(args)[0]
+    return tower, O, tower_image_sizes(cfg)[idx]
+
+
+@pytest.mark.parametrize("kind", ["clip", "dino", "siglip", "convnext"])
+def test_tower_matches_oracle(kind):
+    torch.manual_seed(1)
+    tower, O, R = _tower_pair(kind)
+    with torch.no_grad():  # non-trivial LayerScale / gamma / norm affine so every op is visible
+        for n_, p in tower.named_parameters():
+            if n_.endswith("lambda1") or n_.endswith("gamma"):
+                p.copy_(0.5 + 0.5 * torch.rand_like(p))
+            elif "norm" in n_ and n_.endswith("weight"):
+                p.copy_(1 + 0.2 * torch.randn_like(p))
+    tower = _cuda_bf16(tower)
+    sd = sd_cpu32(tower.vision_tower)
+    img = torch.randn(2, 3, R, R)
+    c = tower.cfg
+    interp = tower._interp_size
+    with torch.no_grad():
+        if kind == "clip":
+            ref = O.clip_vit(sd, dict(num_hidden_layers=c["num_hidden_layers"], patch_size=14,
+                                      num_attention_heads=c["num_attention_heads"], select_layer=-2, interp=interp),
+                             img.bfloat16().float())
+        elif kind == "dino":
+            ref = O.dinov2_vit(sd, dict(num_hidden_layers=c["num_hidden_layers"], patch_size=14,
+                                        num_attention_heads=c["num_attention_heads"], interp=interp), img.bfloat16().float())
+        elif kind == "siglip":
+            ref = O.siglip_vit(sd, dict(num_hidden_layers=c["num_hidden_layers"], patch_size=14,
+                                        num_attention_heads=c["num_attention_heads"], interp=interp), img.bfloat16().float())
+        else:
+            ref = O.convnext_trunk(sd, dict(depths=c["depths"], interp=interp, multi_stage=True), img.bfloat16().float())
+        got = tower(img.to(dev).bfloat16())
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    assert_close_bf16(got, ref, f"{kind} tower", tol=4e-2, cos=0.998)
+
+
+def test_decoder_layer_matches_oracle():
+    from cambrian_b200.model.language_model.cambrian_llama import CBLlamaDecoderLayer, rope_tables
+    from oracle import cambrian_oracle as O
+    torch.manual_seed(2)
+    cfg = tiny_cambrian_config()
+    layer = CBLlamaDecoderLayer(cfg, 0)
+    with torch.no_grad():
+        for p in layer.parameters():
+            if p.dim() == 2:
+                p.normal_(0, 0.05)
+            else:
+                p.copy_(1 + 0.1 * torch.randn_like(p))
+    layer = _cuda_bf16(layer)
+    sd = sd_cpu32(layer, "model.layers.0.")
+    B, S, H = 2, 300, cfg.hidden_size
+    x = torch.randn(B, S, H)
+    pos = torch.stack([torch.arange(S), torch.arange(S).clamp(max=250)])
+    kmask = torch.ones(B, S, dtype=torch.bool)
+    kmask[1, 270:] = False
+    kmask[0, 40:50] = False
+    ocfg = oracle_cfg(cfg)
+    xo = x.bfloat16().float().requires_grad_()
+    cos, sin = O.rope_cos_sin(pos, H // cfg.num_attention_heads, ocfg["rope_theta"])
+    ref = O.llama_layer(sd, "model.layers.0.", xo, cos, sin, kmask, ocfg)
+    dout = torch.randn_like(ref)
+    dout[~kmask] = 0  # padded query rows carry no loss
+    ref.backward(dout.bfloat16().float())
+    cos_t, sin_t = rope_tables(cfg, torch.device(dev))
+    for recompute in (False, True):
+        layer.zero_grad()
+        rt = dict(pos=pos.to(dev).reshape(-1).contiguous(), cos=cos_t, sin=sin_t, kmask=kmask.to(dev), hf_cast=False,
+                  recompute=recompute)
+        xg = x.to(dev).bfloat16().requires_grad_()
+        out = layer(xg, rt)
+        out.backward(dout.to(dev).bfloat16())
+        valid = kmask.to(dev)
+        assert_close_bf16(out[valid], ref[kmask], f"decoder layer fwd (recompute={recompute})")
+        assert_close_bf16(xg.grad[valid], xo.grad[kmask], "decoder layer dx", tol=4e-2, cos=0.998)
+        gref = torch.autograd.grad(
+            O.llama_layer({k: v.requires_grad_() for k, v in sd.items()}, "model.layers.0.", x.bfloat16().float(), cos, sin,
+                          kmask, ocfg), [sd[k] for k in sd], dout.bfloat16().float())
+        name2g = dict(zip(sd.keys(), gref))
+        for k, p in layer.named_parameters():
+            assert_close_bf16(p.grad, name2g["model.layers.0." + k], f"decoder grad {k}", tol=5e-2, cos=0.995)
+
+
+def _build_tiny_model(cfg):
+    from cambrian_b200.model.language_model.cambrian_llama import CambrianLlamaForCausalLM
+    torch.manual_seed(3)
+    cfg.dino_config_overrides = dict(hidden_size=384, num_hidden_layers=2, num_attention_heads=6, mlp_ratio=4)
+    model = CambrianLlamaForCausalLM(cfg)
+    for t in model.get_model().vision_tower_aux_list:
+        t.load_model()
+    with torch.no_grad():
+        for n_, p in model.named_parameters():
+            if "pos_embed" in n_:
+                p.mul_(0.1)
+    model = _cuda_bf16(model)
+    for t in model.get_model().vision_tower_aux_list:
+        t.to(device=dev, dtype=torch.bfloat16)
+    return model
+
+
+def _tiny_batch(cfg, B=2, S=96):
+    g = torch.Generator().manual_seed(7)
+    q = int(cfg.image_token_len ** 0.5)
+    span = q * (q + 1)
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=g)
+    p0 = cfg.image_position
+    ids[:, p0] = -200
+    ids[:, p0 + 1:p0 + span] = 0
+    labels = ids.clone()
+    labels[:, p0:p0 + span] = -100
+    labels[:, :p0] = -100
+    attn = torch.ones(B, S, dtype=torch.bool)
+    attn[1, S - 10:] = False
+    labels[1, S - 10:] = -100
+    pos = (attn.long().cumsum(1) - 1).clamp(min=0)
+    images = [torch.randn(B, 3, r, r, generator=g) for r in tower_image_sizes(cfg)]
+    masks = []
+    for L in cfg.mm_vision_tower_aux_token_len_list:
+        r = int(L ** 0.5) // q
+        mk = torch.rand(B * q * q, r * r, generator=g) > 0.2
+        mk[mk.sum(1) == 0] = True
+        masks.append(mk)
+    return ids, labels, attn, pos, images, masks
+
+
+def _oracle_forward(model, cfg, ids, labels, attn, pos, images, masks):
+    from oracle import cambrian_oracle as O
+    sd = sd_cpu32(model)
+    towers = model.get_model().vision_tower_aux_list
+    bf = lambda t: t.bfloat16().float()
+    feats = []
+    with torch.no_grad():
+        for kind, t, img in zip(("siglip", "clip", "dino", "convnext"), towers, images):
+            tsd = sd_cpu32(t.vision_tower)
+            c = t.cfg
+            common = dict(num_hidden_layers=c.get("num_hidden_layers"), patch_size=14,
+                          num_attention_heads=c.get("num_attention_heads"), interp=t._interp_size)
+            if kind == "siglip":
+                f = O.siglip_vit(tsd, common, bf(img))
+            elif kind == "clip":
+                f = O.clip_vit(tsd, dict(common, select_layer=-2), bf(img))
+            elif kind == "dino":
+                f = O.dinov2_vit(tsd, common, bf(img))
+            else:
+                f = O.convnext_trunk(tsd, dict(depths=c["depths"], interp=t._interp_size, multi_stage=True), bf(img))
+            feats.append(bf(f))  # the CUDA towers hand bf16 features to the trainable part
+    ocfg = oracle_cfg(cfg)
+    sdg = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    img, feats_w, ctx_q = O.connector(sdg, ocfg, feats, masks)
+    emb = O.splice(sdg, ids, img)
+    hid = O.decoder(sdg, ocfg, emb, pos, attn, feats_w, masks, ctx_q)
+    logits, loss = O.lm_loss(sdg, hid, labels)
+    return logits, loss, sdg
+
+
+@pytest.mark.parametrize("fused_loss", [False, True])
+def test_full_model_loss_and_grads_match_oracle(fused_loss):
+    cfg = tiny_cambrian_config()
+    cfg.fused_lm_loss = fused_loss
+    model = _build_tiny_model(cfg)
+    model.train()
+    ids, labels, attn, pos, images, masks = _tiny_batch(cfg)
+    ref_logits, ref_loss, sdg = _oracle_forward(model, cfg, ids, labels, attn, pos, images, masks)
+    ref_loss.backward()
+    out = model(input_ids=ids.to(dev), labels=labels.to(dev), attention_mask=attn.to(dev), position_ids=pos.to(dev),
+                images=[i.to(dev).bfloat16() for i in images], image_aux_attention_masks_list=[m.to(dev) for m in masks])
+    out.loss.backward()
+    assert abs(out.loss.item() - ref_loss.item()) < 2e-2 * abs(ref_loss.item()), (out.loss.item(), ref_loss.item())
+    if not fused_loss:
+        valid = attn[:, :, None].expand_as(ref_logits)
+        assert_close_bf16(out.logits.cpu()[valid], ref_logits[valid], "logits", tol=5e-2, cos=0.995)
+    bad = []
+    for k, p in model.named_parameters():
+        g = sdg[k].grad
+        if g is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, f"missing grad for {k}"
+        e = rel_err(p.grad, g)
+        if e > 8e-2:
+            bad.append((k, e))
+    assert not bad, f"gradient mismatches: {bad[:10]}"
+
+
+def test_engine_step_and_greedy_generate():
+    """TrainEngine (flat buffers, main_grad accumulation, fused AdamW) must reproduce plain-autograd gradients, and
+    greedy generation must be token-exact against the oracle's greedy decode on the same weights."""
+    from cambrian_b200.engine import TrainEngine
+    from oracle import cambrian_oracle as O
+    cfg = tiny_cambrian_config()
+    cfg.fused_lm_loss = True
+    model = _build_tiny_model(cfg)
+    model.train()
+    ids, labels, attn, pos, images, masks = _tiny_batch(cfg)
+    batch = dict(input_ids=ids.to(dev), labels=labels.to(dev), attention_mask=attn.to(dev), position_ids=pos.to(dev),
+                 images=[i.to(dev).bfloat16() for i in images], image_aux_attention_masks_list=[m.to(dev) for m in masks])
+    out = model(**batch)
+    out.loss.backward()
+    ref_grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    eng = TrainEngine(model, lr=1e-3)
+    before = eng.flat_p.clone()
+    eng.zero_grad()
+    loss2 = model(**batch).loss
+    loss2.backward()
+    for k, p in model.named_parameters():
+        if k in ref_grads:
+            assert rel_err(p.main_grad, ref_grads[k]) < 2e-2, k
+    eng.step()
+    assert float((eng.flat_p.float() - before.float()).abs().max()) > 0
+    assert torch.isfinite(eng.master).all()
+    # ---- greedy decode parity (eval numerics: HF rmsnorm cast order)
+    model.eval()
+    S0 = 40
+    gen_ids = ids[:1, :S0].clone()
+    new = model.generate(gen_ids.to(dev), images=[i[:1].to(dev).bfloat16() for i in images], image_sizes=[(56, 56)],
+                         max_new_tokens=4, do_sample=False)
+    sd = sd_cpu32(model)
+    with torch.no_grad():
+        cur_ids, cur_pos = gen_ids.clone(), torch.arange(S0)[None]
+        toks = []
+        ocfg = oracle_cfg(cfg)
+        bf = lambda t: t.bfloat16().float()
+        towers = model.get_model().vision_tower_aux_list
+        feats = [bf(t(i[:1].to(dev).bfloat16()).float().cpu()) for t, i in zip(towers, images)]
+        img, feats_w, ctx_q = O.connector(sd, ocfg, feats, None)
+        emb = O.splice(sd, cur_ids, img)
+        for _ in range(4):
+            hid = O.decoder(sd, ocfg, emb, torch.arange(emb.shape[1])[None], None, feats_w, None, ctx_q)
+            logits, _ = O.lm_loss(sd, hid[:, -1:], None)
+            nxt = int(logits[0, -1].argmax())
+            toks.append(nxt)
+            emb = torch.cat([emb, sd["model.embed_tokens.weight"][nxt][None, None]], 1)
+    assert new.shape == (1, 4)
+    # bf16 vs fp32 argmax can legitimately differ on near-ties; require the first token and >= 3 of 4 to agree
+    got = new[0].tolist()
+    assert got[0] == toks[0] and sum(int(a == b) for a, b in zip(got, toks)) >= 3, (got, toks)
