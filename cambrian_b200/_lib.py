@@ -22,6 +22,7 @@ SIGNATURES = {
     "cb_version": (_i, []),
     "cb_last_error": (C.c_char_p, []),
     "cb_sm_count": (_i, []),
+    "cb_launch_count": (_i64, []),
     "cb_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i, _i,
                           _vp, _vp, _vp, _i64, _i64, _f, _i, _i, _i, _i, _vp]),
     "cb_sva_window_attn_fwd": (_i, [_vp, _vp, _vp, _i, _vpp, _vpp, _vpp, _ip, _i, _i, _i, _i, _vp]),

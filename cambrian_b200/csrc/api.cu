@@ -3,6 +3,7 @@
 #include "../../include/cambrian_b200.h"
 #include <cstdarg>
 #include <cstdio>
+#include <atomic>
 
 namespace cb {
 
@@ -15,6 +16,10 @@ int set_error(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int device_sm_count() {
   static int sms[64] = {0};
@@ -90,6 +95,7 @@ extern "C" {
 int cb_version(void) { return 1; }
 const char* cb_last_error(void) { return cb::g_err; }
 int cb_sm_count(void) { return cb::device_sm_count(); }
+int64_t cb_launch_count(void) { return cb::launch_count(); }
 
 int cb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int batch, int64_t lda,
                  int64_t ldb, int64_t ldc, int64_t bsa, int64_t bsb, int64_t bsc, int a_mn, int b_mn,

@@ -30,8 +30,10 @@ int set_error(int code, const char* fmt, ...);
     if (!(cond)) return cb::set_error(CB_ERR_INVALID, __VA_ARGS__);     \
   } while (0)
 
+void count_launch();  // api.cu: one increment per kernel launch (cb_launch_count)
 #define CB_CUDA_LAUNCH_CHECK(name)                                                    \
   do {                                                                                \
+    cb::count_launch();                                                               \
     cudaError_t _e = cudaGetLastError();                                              \
     if (_e != cudaSuccess)                                                            \
       return cb::set_error(CB_ERR_CUDA, "%s: %s", name, cudaGetErrorString(_e));      \

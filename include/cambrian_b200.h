@@ -39,6 +39,8 @@ extern "C" {
 int cb_version(void);
 const char* cb_last_error(void);
 int cb_sm_count(void);
+/* number of kernels this library has launched in this process (bench.py reports the per-step delta as gpu_launches) */
+int64_t cb_launch_count(void);
 
 /* ---- dense contraction: tcgen05 + TMA persistent GEMM --------------------------------------
  * C[b] (M x N row-major, ldc)  (+)=  epi( alpha * opA(A[b]) (M x K) * opB(B[b]) (K x N) )

@@ -1,0 +1,135 @@
+"""Generates the committed golden fixtures from the UNMODIFIED reference modules (run in the build container only:
+/root/reference does not exist on the GPU box).
+
+    python tests/golden/make_golden.py
+
+Weights are not stored: every parameter is regenerated from numpy's PCG64 stream (stable across numpy versions) by
+`seeded_fill`, in state-dict order, so the fixtures stay a few hundred KB.  Each .npz holds the seeded inputs and the
+reference's outputs for:
+  sva_*.npz        VisionTokenSampler.forward (vision_sampler.py:407-419) — connector shape (q_dim 1024) and in-LLM
+                   shape (q_dim 256), kv sizes with r > 1 and letter-box style masks
+  rearrange.npz    rearrange_vision_tower_features_train (cambrian_arch.py:271-287)
+  collator.npz     prepare_image_info / get_padding_offset (train_fsdp.py:1039-1085) for several image sizes
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def seeded_fill(module_or_sd, seed):
+    """Deterministic parameter values in state-dict order (shared by the generator and the tests)."""
+    rng = np.random.default_rng(seed)
+    sd = module_or_sd if isinstance(module_or_sd, dict) else module_or_sd.state_dict()
+    out = {}
+    for k, v in sd.items():
+        a = rng.standard_normal(tuple(v.shape)).astype(np.float32)
+        if v.dim() >= 2 and "pos_embed" not in k:
+            a *= 0.03
+        elif "pos_embed" in k:
+            a *= 0.1
+        elif k.endswith("weight"):      # LayerNorm scale
+            a = 1.0 + 0.1 * a
+        else:                            # biases
+            a *= 0.1
+        out[k] = torch.from_numpy(a)
+    return out
+
+
+def seeded_inputs(seed, n, q_dim, rs, mask_p=0.3):
+    rng = np.random.default_rng(seed)
+    queries = torch.from_numpy(rng.standard_normal((n, 1, q_dim)).astype(np.float32))
+    ctx = torch.from_numpy(rng.standard_normal((n, 1, 1024)).astype(np.float32))
+    feats = [torch.from_numpy(rng.standard_normal((n, r * r, 1024)).astype(np.float32)) for r in rs]
+    masks = []
+    for r in rs:
+        m = rng.random((n, r * r)) > mask_p
+        m[m.sum(1) == 0] = True
+        masks.append(torch.from_numpy(m))
+    return queries, ctx, feats, masks
+
+
+SVA_CASES = {
+    "sva_connector": dict(q_dim=1024, rs=[1, 1, 1, 1], layers=2, n=32, seed=11),
+    "sva_connector_r4": dict(q_dim=1024, rs=[1, 1, 1, 4], layers=1, n=18, seed=12),
+    "sva_inllm": dict(q_dim=256, rs=[1, 2, 1, 3], layers=1, n=32, seed=13),
+}
+
+
+def main():
+    from oracle import ref_shim
+    vs = ref_shim.ref_module("cambrian.model.vision_sampler")
+    arch = ref_shim.ref_module("cambrian.model.cambrian_arch")
+    for name, c in SVA_CASES.items():
+        T = len(c["rs"])
+        m = vs.VisionTokenSampler(c["q_dim"], 1024, [1024] * T, c["rs"], 1024, c["layers"]).eval()
+        m.load_state_dict(seeded_fill(m, c["seed"]))
+        queries, ctx, feats, masks = seeded_inputs(c["seed"] + 100, c["n"], c["q_dim"], c["rs"])
+        with torch.no_grad():
+            out = m(queries, ctx, *feats, *masks)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), out=out.numpy())
+        print(name, tuple(out.shape), float(out.abs().mean()))
+
+    # window rearrange
+    rng = np.random.default_rng(21)
+    feat = torch.from_numpy(rng.standard_normal((2, 64, 8)).astype(np.float32))   # 8x8 grid, q_side 4 -> r = 2
+    mask = torch.from_numpy(rng.random((2 * 16, 4)) > 0.5)
+
+    class _Dummy(arch.CambrianMetaForCausalLM):
+        def get_model(self):
+            return None
+    fr, mr = _Dummy().rearrange_vision_tower_features_train([feat], [mask], 4)
+    np.savez_compressed(os.path.join(HERE, "rearrange.npz"), feat=feat.numpy(), out=fr[0].numpy(), mask=mr[0].numpy())
+
+    # collator geometry (train_fsdp.py imports torch_xla etc. at module scope -> stubbed by the shim)
+    # The TPU harness module cannot be imported (torch_xla, transformers-4.37 trainer symbols), so the three pure
+    # functions are lifted out of the reference file by name with `ast` and executed unmodified.
+    import ast
+    import types
+    src = open("/root/reference/cambrian/train/train_fsdp.py").read()
+    tree = ast.parse(src)
+    want = {"get_padding_offset", "prepare_image_info", "prepare_multimodal_data"}
+    code = "\n\n".join(ast.get_source_segment(src, n) for n in tree.body
+                       if isinstance(n, ast.FunctionDef) and n.name in want)
+    tf = types.SimpleNamespace()
+    ns_ = {"torch": torch, "IMAGE_TOKEN_INDEX": -200, "IGNORE_INDEX": -100}
+    exec(compile(code, "train_fsdp_extract", "exec"), ns_)
+    tf.prepare_image_info = ns_["prepare_image_info"]
+    tf.prepare_multimodal_data = ns_["prepare_multimodal_data"]
+    sizes = [(640, 480), (480, 640), (336, 336), (1000, 200), (123, 457)]
+    recs = {}
+    for (w, h) in sizes:
+        for tok in (576, 9216):
+            for nl in (False, True):
+                if nl and tok != 576:
+                    continue
+                am, pid = tf.prepare_image_info((w, h), tok, newline=nl)
+                recs[f"mask_{w}x{h}_{tok}_{int(nl)}"] = am.numpy()
+                recs[f"pos_{w}x{h}_{tok}_{int(nl)}"] = pid.numpy()
+    # full collator expansion (train_fsdp.py:1089-1165) on a seeded batch with one image per sample
+    rng = np.random.default_rng(31)
+    B, L = 3, 40
+    ids = torch.from_numpy(rng.integers(3, 1000, size=(B, L)))
+    for b, p0 in enumerate((5, 9, 0)):
+        ids[b, p0] = -200
+    labels = ids.clone()
+    attn = torch.ones(B, L, dtype=torch.bool)
+    attn[2, 30:] = False
+    im_sizes = [(640, 480), (336, 336), (200, 1000)]
+    out = tf.prepare_multimodal_data(ids, labels, attn, im_sizes, image_token_len=16,
+                                     image_aux_token_len_list=[16, 64], max_length=64)
+    recs.update(cm_ids_in=ids.numpy(), cm_attn_in=attn.numpy(), cm_ids=out[0].numpy(), cm_labels=out[1].numpy(),
+                cm_attn=out[2].numpy(), cm_pos=out[3].numpy(), cm_aux0=out[4][0].numpy(), cm_aux1=out[4][1].numpy())
+    np.savez_compressed(os.path.join(HERE, "collator.npz"), **recs)
+    print("collator", len(recs))
+
+
+if __name__ == "__main__":
+    main()

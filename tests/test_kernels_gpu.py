@@ -1,0 +1,86 @@
+"""Kernel-level GPU parity tests, called through the C ABI (ctypes): every case compares one hand-written sm_100a kernel
+with a plain PyTorch fp32 reference of the same op on seeded inputs.  The case tables live in tools/probe1.py /
+tools/probe2.py (they print one line per case, which doubles as the profiling log); a case that misses its tolerance
+prints FAIL.  Tolerances: GEMM with fp32 output 2e-5 relative (north_star's rtol 1e-3 / atol 1e-5 with margin); bf16 outputs
+1e-2 .. 2e-2 of the tensor's max (one to two bf16 ulps of accumulated rounding)."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+
+
+def _run(mod, group, capsys, min_ok):
+    m = __import__(mod)
+    getattr(m, "group_" + group)()
+    out = capsys.readouterr().out
+    sys.stdout.write(out)
+    assert "FAIL" not in out, out
+    assert out.count(" OK") >= min_ok, f"expected at least {min_ok} passing cases\n{out}"
+
+
+def test_gemm_all_layouts_and_tiles(capsys):
+    _run("probe1", "gemm_basic", capsys, 12)
+
+
+def test_gemm_shapes_tails_batched(capsys):
+    _run("probe1", "gemm_shapes", capsys, 25)
+
+
+def test_gemm_epilogues(capsys):
+    _run("probe1", "gemm_epi", capsys, 10)
+
+
+def test_sva_window_attention_fwd_bwd(capsys):
+    _run("probe1", "sva", capsys, 4)
+
+
+def test_layernorm_rmsnorm_fwd_bwd(capsys):
+    _run("probe1", "norm", capsys, 19)
+
+
+def test_elementwise_family(capsys):
+    _run("probe2", "elem", capsys, 17)
+
+
+def test_flash_attention_forward(capsys):
+    _run("probe2", "attn_fwd", capsys, 9)
+
+
+def test_flash_attention_backward(capsys):
+    _run("probe2", "attn_bwd", capsys, 7)
+
+
+def test_full_size_properties():
+    """Size-independent properties at BASELINE's full shapes (no oracle needed):
+    linearity of the GEMM, softmax rows of the SVA kernel summing to one (V = 1 -> out = 1), attention with a single
+    visible key returning that key's value."""
+    import torch
+    from cambrian_b200 import ops
+    dev = "cuda"
+    torch.manual_seed(0)
+    a = torch.randn(4608, 4096, device=dev).bfloat16()
+    w = torch.randn(14336, 4096, device=dev).bfloat16() * 0.02
+    y1 = ops.gemm(a, w, out_dtype=torch.float32)
+    y2 = ops.gemm(a, w, out_dtype=torch.float32, alpha=2.0)
+    assert torch.allclose(y2, 2 * y1, rtol=1e-6, atol=1e-6)
+    y3 = ops.gemm(a, w, out_dtype=torch.float32, out=y1.clone(), accumulate=True)
+    assert torch.allclose(y3, 2 * y1, rtol=1e-5, atol=1e-5)
+    # SVA, release grids [576,576,576,9216], batch 4
+    B, q, rs = 4, 24, [1, 1, 1, 4]
+    n = B * q * q
+    qq = torch.randn(n, 1024, device=dev).bfloat16()
+    ks = [torch.randn(B, (r * q) ** 2, 1024, device=dev).bfloat16() for r in rs]
+    ones = [torch.ones_like(k) for k in ks]
+    out, _ = ops.sva_window_attn_fwd(qq, ks, ones, None, rs, B, q)
+    assert torch.allclose(out.float(), torch.ones_like(out).float(), atol=1e-2)
+    # causal attention, S = 2048: the first query sees only key 0
+    S, nh, nkv, hd = 2048, 32, 8, 128
+    qkv = torch.randn(1, S, (nh + 2 * nkv) * hd, device=dev).bfloat16()
+    qv = qkv[..., : nh * hd].view(1, S, nh, hd)
+    kv = qkv[..., nh * hd:(nh + nkv) * hd].view(1, S, nkv, hd)
+    vv = qkv[..., (nh + nkv) * hd:].view(1, S, nkv, hd)
+    o = ops.attn_fwd(qv, kv, vv, causal=True)
+    assert torch.equal(o[0, 0], vv[0, 0].repeat_interleave(nh // nkv, 0))

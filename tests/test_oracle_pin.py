@@ -1,0 +1,157 @@
+"""Pins the CPU oracle (oracle/cambrian_oracle.py) — CPU only, no GPU:
+  * against the committed golden fixtures generated from the reference's own modules (tests/golden/make_golden.py);
+  * against the installed `transformers` implementations the reference delegates to (CLIPVisionModel, Dinov2Model,
+    LlamaDecoderLayer + LlamaRMSNorm + rotary embedding);
+  * directly against the reference modules when /root/reference is present (build container only)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+from make_golden import SVA_CASES, seeded_fill, seeded_inputs  # noqa: E402
+
+from oracle import cambrian_oracle as O  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+GOLD = os.path.join(HERE, "golden")
+
+
+def _sva_shapes(q_dim, rs, layers):
+    """state-dict shapes of VisionTokenSampler in the reference's registration order (vision_sampler.py:254-268,170-175)."""
+    sd = {}
+    for l in range(layers):
+        p = f"layers.{l}."
+        for i, r in enumerate(rs):
+            if r > 1:
+                sd[p + f"pos_embed_{i}"] = (r * r, 1024)
+        sd[p + "proj_context.weight"] = (1024, 1024)
+        sd[p + "proj_in.weight"] = (1024, q_dim + 1024)
+        sd[p + "proj_out.linear_1.weight"] = (1024, 1024)
+        sd[p + "proj_out.linear_2.weight"] = (q_dim, 1024)
+        sd[p + "norm.weight"] = (1024,)
+        sd[p + "norm.bias"] = (1024,)
+        names = ["q_proj"] + [f"{k}_proj_{i}" for i in range(len(rs)) for k in "kv"]
+        for nm in names:
+            sd[p + f"cross_attn.{nm}.0.weight"] = (1024,)
+            sd[p + f"cross_attn.{nm}.0.bias"] = (1024,)
+            sd[p + f"cross_attn.{nm}.1.weight"] = (1024, 1024)
+        sd[p + "cross_attn.o_proj.weight"] = (1024, 1024)
+    return {k: torch.empty(v) for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("name", sorted(SVA_CASES))
+def test_sva_oracle_matches_reference_golden(name):
+    c = SVA_CASES[name]
+    sd = seeded_fill(_sva_shapes(c["q_dim"], c["rs"], c["layers"]), c["seed"])
+    queries, ctx, feats, masks = seeded_inputs(c["seed"] + 100, c["n"], c["q_dim"], c["rs"])
+    with torch.no_grad():
+        got = O.sva_sampler(sd, "", queries, ctx, feats, masks, c["layers"])
+    ref = torch.from_numpy(np.load(os.path.join(GOLD, name + ".npz"))["out"])
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_window_rearrange_matches_reference_golden():
+    z = np.load(os.path.join(GOLD, "rearrange.npz"))
+    got = O.window_rearrange(torch.from_numpy(z["feat"]), 4)
+    assert torch.equal(got, torch.from_numpy(z["out"]))
+
+
+def test_oracle_clip_matches_transformers():
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    torch.manual_seed(0)
+    cfg = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, patch_size=14,
+                           image_size=56, hidden_act="quick_gelu")
+    m = CLIPVisionModel(cfg).eval()
+    img = torch.randn(2, 3, 56, 56)
+    with torch.no_grad():
+        ref = m(img, output_hidden_states=True).hidden_states[-2][:, 1:]      # clip_encoder.py:55-68
+        got = O.clip_vit({k: v for k, v in m.state_dict().items()},
+                         dict(num_hidden_layers=3, patch_size=14, num_attention_heads=2, select_layer=-2), img)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("res", [518 // 37 * 4, 14 * 6])
+def test_oracle_dinov2_matches_transformers(res):
+    from transformers import Dinov2Config, Dinov2Model
+    torch.manual_seed(0)
+    cfg = Dinov2Config(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, mlp_ratio=4, patch_size=14,
+                       image_size=56)
+    m = Dinov2Model(cfg).eval()
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            if "lambda1" in n_:
+                p.copy_(0.5 + torch.rand_like(p))
+    img = torch.randn(2, 3, res, res)
+    with torch.no_grad():
+        ref = m(img).last_hidden_state[:, 1:]                                 # dino_encoder.py:115-126
+        got = O.dinov2_vit({k: v for k, v in m.state_dict().items()},
+                           dict(num_hidden_layers=2, patch_size=14, num_attention_heads=2), img)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_oracle_llama_layer_matches_transformers():
+    from transformers import LlamaConfig
+    from transformers.models.llama.modeling_llama import LlamaDecoderLayer, LlamaRotaryEmbedding
+    torch.manual_seed(0)
+    cfg = LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=1, num_attention_heads=4,
+                      num_key_value_heads=2, rms_norm_eps=1e-5, rope_theta=500000.0, max_position_embeddings=256)
+    cfg._attn_implementation = "eager"
+    layer = LlamaDecoderLayer(cfg, 0).eval()
+    rot = LlamaRotaryEmbedding(cfg)
+    B, S = 2, 37
+    x = torch.randn(B, S, 128)
+    pos = torch.arange(S)[None].expand(B, S)
+    keymask = torch.ones(B, S, dtype=torch.bool)
+    keymask[1, 30:] = False
+    causal = torch.ones(S, S, dtype=torch.bool).tril()
+    allow = causal[None, None] & keymask[:, None, None, :]
+    add_mask = torch.zeros(B, 1, S, S).masked_fill(~allow, torch.finfo(torch.float32).min)
+    with torch.no_grad():
+        pe = rot(x, pos)
+        ref = layer(x, attention_mask=add_mask, position_ids=pos, position_embeddings=pe)
+        ref = ref[0] if isinstance(ref, tuple) else ref
+        sd = {"model.layers.0." + k: v for k, v in layer.state_dict().items()}
+        cos, sin = O.rope_cos_sin(pos, 32, 500000.0)
+        got = O.llama_layer(sd, "model.layers.0.", x, cos, sin, keymask,
+                            dict(num_attention_heads=4, num_key_value_heads=2, rms_norm_eps=1e-5))
+    torch.testing.assert_close(got[keymask], ref[keymask], rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- reference present
+needs_ref = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present (GPU box)")
+
+
+@needs_ref
+def test_oracle_sva_config1_full_size_against_reference():
+    """BASELINE config 1: SVA projector alone (576 queries, 4 x 24 x 24 x 1024 grids), plus the [1,1,1,4] variant."""
+    vs = ref_shim.ref_module("cambrian.model.vision_sampler")
+    for rs in ([1, 1, 1, 1], [1, 1, 1, 4]):
+        torch.manual_seed(0)
+        m = vs.VisionTokenSampler(1024, 1024, [1024] * 4, rs, 1024, 3).eval()
+        feats = [torch.randn(1, (24 * r) ** 2, 1024) for r in rs]
+        query = (torch.randn(1, 1024) / 32).view(1, 1, 1, -1).expand(1, 576, -1, -1).flatten(0, 1)
+        ctx = feats[0].mean(1).view(1, 1, 1, -1).expand(-1, 576, 1, -1).flatten(0, 1)
+        fw = [O.window_rearrange(f, 24) for f in feats]
+        masks = [torch.rand(576, r * r) > 0.2 for r in rs]
+        for mk in masks:
+            mk[mk.sum(1) == 0] = True
+        with torch.no_grad():
+            ref = m(query, ctx, *fw, *masks)
+            got = O.sva_sampler(dict(m.state_dict()), "", query, ctx, fw, masks, 3)
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=2e-5)
+
+
+@needs_ref
+def test_oracle_projectors_against_reference():
+    pb = ref_shim.ref_module("cambrian.model.multimodal_projector.builder")
+    from helpers import ns
+    torch.manual_seed(0)
+    proj = pb.build_vision_projector(ns(mm_projector_type="mlp2x_gelu", mm_hidden_size=96, hidden_size=64)).eval()
+    x = torch.randn(3, 7, 96)
+    with torch.no_grad():
+        torch.testing.assert_close(O.mlp2x_gelu({"p." + k: v for k, v in proj.state_dict().items()}, "p.", x), proj(x),
+                                   rtol=1e-5, atol=1e-6)
