@@ -1,0 +1,184 @@
+"""CPU tests of the host-side logic: collator mirror vs golden fixtures from the reference functions, tower-name
+parsing / builder dispatch / error conventions, fused-parameter storage, image-token expansion, TrainEngine flat layout,
+and the data-parallel gradient reduction on a 2-process gloo group."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+sys.path.insert(0, HERE)
+from helpers import ns, tiny_cambrian_config  # noqa: E402
+
+
+# ------------------------------------------------------------------------------------------------ collator (bit-exact)
+def test_prepare_image_info_matches_reference_golden():
+    from cambrian_b200.train.collator import prepare_image_info
+    z = np.load(os.path.join(GOLD, "collator.npz"))
+    n = 0
+    for key in z.files:
+        if not key.startswith("mask_"):
+            continue
+        _, wh, tok, nl = key.split("_")
+        w, h = map(int, wh.split("x"))
+        m, p = prepare_image_info((w, h), int(tok), newline=bool(int(nl)))
+        assert np.array_equal(m.numpy(), z[key]), key
+        assert np.array_equal(p.numpy(), z["pos_" + key[5:]]), key
+        n += 1
+    assert n >= 15
+
+
+def test_prepare_multimodal_data_matches_reference_golden():
+    from cambrian_b200.train.collator import prepare_multimodal_data
+    z = np.load(os.path.join(GOLD, "collator.npz"))
+    ids = torch.from_numpy(z["cm_ids_in"])
+    attn = torch.from_numpy(z["cm_attn_in"])
+    out = prepare_multimodal_data(ids, ids.clone(), attn, [(640, 480), (336, 336), (200, 1000)], image_token_len=16,
+                                  image_aux_token_len_list=[16, 64], max_length=64)
+    for got, key in zip(out[:4], ("cm_ids", "cm_labels", "cm_attn", "cm_pos")):
+        assert np.array_equal(got.numpy(), z[key]), key
+    assert np.array_equal(out[4][0].numpy(), z["cm_aux0"])
+    assert np.array_equal(out[4][1].numpy(), z["cm_aux1"])
+
+
+def test_collator_edge_cases():
+    from cambrian_b200.train.collator import get_padding_offset, prepare_multimodal_data
+    assert get_padding_offset((24, 24), (336, 336)) == (0, 0, 0, 0)
+    l, r, t, b = get_padding_offset((24, 24), (1000, 10))      # extreme aspect ratio: almost everything padded
+    assert (l, r) == (0, 0) and t == b == 12                   # int(10 * 24/1000) = 0 visible rows
+    ids = torch.tensor([[5, 6, 7]])
+    with pytest.raises(AssertionError):                         # exactly one image per sample (train_fsdp.py:1100)
+        prepare_multimodal_data(ids, ids, torch.ones_like(ids, dtype=torch.bool), [(10, 10)], 16, [16], 64)
+    # truncation to max_length
+    ids = torch.full((1, 60), 9)
+    ids[0, 50] = -200
+    o = prepare_multimodal_data(ids, ids.clone(), torch.ones_like(ids, dtype=torch.bool), [(10, 10)], 16, [16], 64)
+    assert o[0].shape == (1, 64) and o[3].shape == (1, 64)
+
+
+# ------------------------------------------------------------------------------------------------ builders / parsing
+def test_tower_name_parsing_and_dispatch():
+    from cambrian_b200.model.multimodal_encoder.builder import build_vision_tower_aux_list
+    from cambrian_b200.model.multimodal_encoder.towers import (CLIPConvNextTower, ClipVisionTower, DinoVisionTower,
+                                                               SiglipVisionTower, _parse_res_interp)
+    assert _parse_res_interp("facebook/dinov2-large-res336-interp576") == ("facebook/dinov2-large", 336, 576)
+    assert _parse_res_interp("openai/clip-vit-large-patch14-336-interp576") == ("openai/clip-vit-large-patch14-336", None, 576)
+    cfg = ns(mm_vision_tower_aux_list=["siglip/CLIP-ViT-SO400M-14-384", "openai/clip-vit-large-patch14-336",
+                                       "facebook/dinov2-large-res336", "clip-convnext-XXL-multi-stage"],
+             mm_vision_tower_aux_token_len_list=[576, 576, 576, 9216])
+    towers = build_vision_tower_aux_list(cfg, delay_load=True)
+    assert [type(t) for t in towers] == [SiglipVisionTower, ClipVisionTower, DinoVisionTower, CLIPConvNextTower]
+    assert [t.hidden_size for t in towers] == [1152, 1024, 1024, 5760]
+    assert [t.num_patches for t in towers] == [576, 576, 576, 9216]
+    assert [t.image_size for t in towers] == [384, 336, 336, 1024]
+    assert towers[3].is_multi_stage and not towers[0].is_loaded
+    with pytest.raises(ValueError, match="Unknown vision tower"):        # builder.py:147
+        build_vision_tower_aux_list(ns(mm_vision_tower_aux_list=["acme/unknown"], mm_vision_tower_aux_token_len_list=[576]))
+
+
+def test_projector_builder_keys_and_errors():
+    from cambrian_b200.model.multimodal_projector.builder import build_vision_projector
+    p = build_vision_projector(ns(mm_projector_type="mlp2x_gelu", mm_hidden_size=1024, hidden_size=4096))
+    assert sorted(p.state_dict()) == ["0.bias", "0.weight", "2.bias", "2.weight"]
+    assert p.state_dict()["0.weight"].shape == (4096, 1024)
+    assert build_vision_projector(ns(mm_projector_type="linear", mm_hidden_size=8, hidden_size=16)).weight.shape == (16, 8)
+    with pytest.raises(ValueError, match="Unknown projector type"):      # multimodal_projector/builder.py:78
+        build_vision_projector(ns(mm_projector_type="qformer", mm_hidden_size=8, hidden_size=8))
+
+
+def test_sampler_rejects_unsupported_configs():
+    from cambrian_b200.model.vision_sampler import VisionTokenSampler
+    with pytest.raises(NotImplementedError):
+        VisionTokenSampler(64, 1024, [1024], [1], 1024, 1, layer_type="sep")
+    with pytest.raises(NotImplementedError):
+        VisionTokenSampler(64, 512, [512], [1], 512, 1)
+    with pytest.raises(AssertionError):
+        VisionTokenSampler(64, 1024, [1024], [1], 1024, 1, layer_type="bogus")
+
+
+# ------------------------------------------------------------------------------------------------ model plumbing
+def test_state_dict_keys_follow_the_reference_layout():
+    from cambrian_b200.model.language_model.cambrian_llama import CambrianLlamaForCausalLM
+    cfg = tiny_cambrian_config()
+    m = CambrianLlamaForCausalLM(cfg)
+    keys = set(m.state_dict())
+    for k in ["model.embed_tokens.weight", "model.layers.0.self_attn.q_proj.weight", "model.layers.3.mlp.down_proj.weight",
+              "model.norm.weight", "lm_head.weight", "model.mm_projector.0.weight", "model.mm_projector.2.bias",
+              "model.mm_projector_aux_3.3.weight", "model.vision_sampler_0.layers.1.cross_attn.k_proj_2.1.weight",
+              "model.vision_sampler_layers.1.layers.0.proj_in.weight", "model.vision_sampler_layers.0.layers.0.pos_embed_3",
+              "model.vision_query", "model.image_newline"]:
+        assert k in keys, k
+    assert not any("vision_tower" in k for k in keys)       # frozen towers are not part of the state dict (cambrian_arch.py:125-128)
+    assert m.get_model().vision_sampler_layers[0].layers[0].proj_in.weight.shape == (1024, cfg.hidden_size + 1024)
+
+
+def test_fuse_rows_repoints_parameters_once():
+    from cambrian_b200.model.language_model.cambrian_llama import CBLlamaDecoderLayer, _adjacent
+    layer = CBLlamaDecoderLayer(tiny_cambrian_config(), 0)
+    a = layer.self_attn
+    before = [p.detach().clone() for p in (a.q_proj.weight, a.k_proj.weight, a.v_proj.weight)]
+    qkv, gu, _, _ = layer._fused()
+    assert qkv.shape == (256 + 128 + 128, 256) and gu.shape == (1024, 256)
+    assert _adjacent([a.q_proj.weight.data, a.k_proj.weight.data, a.v_proj.weight.data])
+    assert torch.equal(qkv, torch.cat(before, 0))
+    ptr = qkv.data_ptr()
+    qkv2, *_ = layer._fused()
+    assert qkv2.data_ptr() == ptr                           # already adjacent: no new copy
+    a.k_proj.weight.data = a.k_proj.weight.data.clone()     # e.g. after load_state_dict / .to(): adjacency broken
+    qkv3, *_ = layer._fused()
+    assert torch.equal(qkv3, torch.cat(before, 0)) and a.k_proj.weight.data_ptr() != 0
+
+
+def test_expand_image_tokens_matches_collator():
+    from cambrian_b200.model.cambrian_arch import _expand_image_tokens
+    from cambrian_b200.train.collator import prepare_multimodal_data
+    ids = torch.randint(3, 100, (2, 30))
+    ids[0, 4] = -200
+    ids[1, 11] = -200
+    attn = torch.ones_like(ids, dtype=torch.bool)
+    e_ids, e_lab, e_mask, e_pos = _expand_image_tokens(ids, ids.clone(), attn, 20, "cpu")
+    c = prepare_multimodal_data(ids, ids.clone(), attn, [(64, 64), (64, 64)], 16, [16], 1000)
+    assert torch.equal(e_ids, c[0]) and torch.equal(e_lab, c[1]) and torch.equal(e_mask, c[2]) and torch.equal(e_pos, c[3])
+
+
+# ------------------------------------------------------------------------------------------------ data parallel
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cambrian_b200 import engine as E
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(16, 24, bias=True), torch.nn.Linear(24, 8, bias=False)).bfloat16()
+    eng = E.TrainEngine(model, bucket_mb=0.0005)  # tiny buckets -> several all-reduces
+    assert eng.world == world and len(eng.buckets) >= 2
+    # flat layout: parameters are views of one buffer in named_parameters() order, 8-element aligned
+    off = 0
+    for p in eng.params:
+        assert p.data_ptr() == eng.flat_p.data_ptr() + 2 * off and p.main_grad.data_ptr() == eng.flat_g.data_ptr() + 2 * off
+        off += (p.numel() + 7) // 8 * 8
+    eng.zero_grad()
+    for i, p in enumerate(eng.params):
+        p.main_grad.fill_(float(rank + 1) * (i + 1))
+        p._cb_fresh.add("all")
+    eng.reduce_gradients()
+    ok = all(torch.allclose(p.main_grad.float(), torch.full_like(p.main_grad, 3.0 * (i + 1)).float())
+             for i, p in enumerate(eng.params))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
