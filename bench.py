@@ -439,6 +439,7 @@ def main():
                         "optimizer": "AdamW fp32 master + bf16 grads, fused", "trainable_params": n_train,
                         "frozen_tower_params": n_tower, "l2_policy": "inputs larger than L2 (16 GB weights streamed per pass)"},
                 gpu_launches=int(launches), loss=float(loss),
+                peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=4),
                 clocks=sampler.summary(), roofline=roof, roofline_sva=roof_sva,
                 model_tflops_per_gpu=(model_tf / world) if model_tf else None,

@@ -519,7 +519,7 @@ cross_entropy_kernel(bf16* __restrict__ logits, const long long* __restrict__ la
     }
     // block combine (max, sum)
     const float wm = warp_max(m);
-    s *= __expf(m - wm);
+    s = (m == -INFINITY) ? 0.f : s * __expf(m - wm);  // threads without elements (V/8 < blockDim) hold (-inf, 0)
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) { red_m[threadIdx.x >> 5] = wm; red_s[threadIdx.x >> 5] = s; }
     __syncthreads();
@@ -527,7 +527,7 @@ cross_entropy_kernel(bf16* __restrict__ logits, const long long* __restrict__ la
     float bm = -INFINITY;
     for (int k = 0; k < nw; ++k) bm = fmaxf(bm, red_m[k]);
     float bs = 0.f;
-    for (int k = 0; k < nw; ++k) bs += red_s[k] * __expf(red_m[k] - bm);
+    for (int k = 0; k < nw; ++k) bs += (red_m[k] == -INFINITY) ? 0.f : red_s[k] * __expf(red_m[k] - bm);
     m = bm;
     s = bs;
     if (threadIdx.x == 0) loss_rows[row] = (m + logf(s)) - __bfloat162float(lp[label]);
@@ -686,7 +686,9 @@ int bilinear_launch(const void* in, void* out, int B, int h, int w, int th, int 
   return CB_OK;
 }
 int patchify_nchw_launch(const void* img, void* out, int B, int Cin, int R, int p, int Kpad, cudaStream_t st) {
-  CB_CHECK_ARG(R % p == 0 && Kpad >= Cin * p * p && Kpad % 8 == 0, "patchify: R %% p != 0 or bad Kpad");
+  // R need not be a multiple of p: like a stride-p convolution, the trailing R % p pixels are dropped
+  // (SigLIP 384 / 14 -> 27 x 27 patches)
+  CB_CHECK_ARG(R >= p && Kpad >= Cin * p * p && Kpad % 8 == 0, "patchify: image smaller than the patch or bad Kpad");
   const int g = R / p;
   patchify_nchw_kernel<<<grid_for((long long)B * g * g * Kpad, 256), 256, 0, st>>>((const bf16*)img, (bf16*)out, B, Cin, R,
                                                                                   p, Kpad);

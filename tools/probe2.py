@@ -260,23 +260,23 @@ def group_elem():
     print(f"reductions errs={e1:.2e},{e2:.2e},{e3:.2e},{e4:.2e},{e5:.2e} "
           f"{'OK' if max(e1, e2, e3, e4, e5) < 1e-2 else 'FAIL'}", flush=True)
     # cross entropy
-    rows, V = 300, 32000
-    logits = (3 * torch.randn(rows, V, device=dev)).bfloat16()
-    labels = torch.randint(0, V, (rows,), device=dev)
-    labels[::7] = -100
-    lf = logits.float().requires_grad_()
-    ref = F.cross_entropy(lf, labels, ignore_index=-100, reduction="sum")
-    ref.backward()
-    loss_rows = torch.empty(rows, device=dev)
-    acc = torch.zeros(2, device=dev)
-    buf = logits.clone()
-    ops.cross_entropy(buf, labels, loss_rows, acc, 1.0, True)
-    torch.cuda.synchronize()
-    e1 = abs(acc[0].item() - ref.item()) / ref.item()
-    e2 = rel_err(buf, lf.grad)
-    cnt = int((labels != -100).sum())
-    print(f"cross_entropy loss_err={e1:.2e} grad_err={e2:.2e} count={acc[1].item()}/{cnt} "
-          f"{'OK' if e1 < 1e-4 and e2 < 1e-2 and acc[1].item() == cnt else 'FAIL'}", flush=True)
+    for rows, V in ((300, 32000), (192, 1024), (64, 128256)):  # incl. V/8 < blockDim (idle threads) and the Llama-3 vocab
+        logits = (3 * torch.randn(rows, V, device=dev)).bfloat16()
+        labels = torch.randint(0, V, (rows,), device=dev)
+        labels[::7] = -100
+        lf = logits.float().requires_grad_()
+        ref = F.cross_entropy(lf, labels, ignore_index=-100, reduction="sum")
+        ref.backward()
+        loss_rows = torch.empty(rows, device=dev)
+        acc = torch.zeros(2, device=dev)
+        buf = logits.clone()
+        ops.cross_entropy(buf, labels, loss_rows, acc, 1.0, True)
+        torch.cuda.synchronize()
+        e1 = abs(acc[0].item() - ref.item()) / ref.item()
+        e2 = rel_err(buf, lf.grad)
+        cnt = int((labels != -100).sum())
+        print(f"cross_entropy loss_err={e1:.2e} grad_err={e2:.2e} count={acc[1].item()}/{cnt} "
+              f"{'OK' if e1 < 1e-4 and e2 < 1e-2 and acc[1].item() == cnt else 'FAIL'}", flush=True)
     # adamw vs torch
     n = 1 << 16
     p = torch.randn(n, device=dev)
