@@ -339,11 +339,12 @@ def main():
     host_batches = [make_host_batch(cfg, B, S, 1000 * rank + i, res) for i in range(2)]
     dev_batch, h2d_bytes = to_device(host_batches[0][0], dev)
     n_valid = host_batches[0][1]
+    img_pos = [cfg.image_position] * B  # known to the collator (train_fsdp.py:1089-1165); avoids a D2H scan per step
     torch.cuda.synchronize()
 
     def step_resident():
         engine.zero_grad()
-        out = model(**dev_batch, num_valid_labels=n_valid)
+        out = model(**dev_batch, num_valid_labels=n_valid, image_positions=img_pos)
         out.loss.backward()
         engine.step()
         return out.loss
@@ -352,7 +353,7 @@ def main():
         hb, nv = host_batches[i % 2]
         db, _ = to_device(hb, dev)
         engine.zero_grad()
-        out = model(**db, num_valid_labels=nv)
+        out = model(**db, num_valid_labels=nv, image_positions=img_pos)
         out.loss.backward()
         engine.step()
         return float(out.loss.item())  # device -> host read of the step's result

@@ -86,8 +86,17 @@ class TrainEngine:
         self._handles = []
 
     def _finalize_unwritten(self):
-        """Parameters that received no gradient this step (unused modules) must not feed stale values to Adam."""
+        """Fold in gradients that reached a parameter through plain autograd (a parameter used by an ordinary torch
+        view/op, e.g. the `vision_query[g:g+1]` slice), then zero parameters that received no gradient at all this step
+        (unused modules) so they do not feed stale values to Adam."""
         for p in self.params:
+            if p.grad is not None:
+                if p._cb_fresh:
+                    p.main_grad.add_(p.grad.to(p.main_grad.dtype))
+                else:
+                    p.main_grad.copy_(p.grad)
+                    p._cb_fresh.add("all")
+                p.grad = None
             if not p._cb_fresh:
                 p.main_grad.zero_()
 

@@ -108,7 +108,10 @@ class CambrianMetaForCausalLM(ABC):
         return [tower(img) for img, tower in zip(image_aux_list, self.get_model().get_vision_tower_aux_list())]
 
     def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
-                                             images, image_aux_attention_masks_list=None, image_sizes=None):
+                                             images, image_aux_attention_masks_list=None, image_sizes=None,
+                                             image_positions=None):
+        """`image_positions` (extension, host ints): index of the <image> indicator of every sample of an ALREADY
+        expanded batch (what the collator knows); skips the device->host scan of input_ids (a stream sync)."""
         model = self.get_model()
         towers = model.get_vision_tower_aux_list()
         if towers is None or images is None or input_ids.shape[1] == 1:                          # :345-346
@@ -123,25 +126,28 @@ class CambrianMetaForCausalLM(ABC):
         span = q_num + q_side
         # --- locate the image span of every sample; expand a bare <image> indicator the way the collator does
         #     (train_fsdp.py:1089-1165) when the caller passes un-expanded ids (inference path)
-        ids_cpu = input_ids.detach().to("cpu")
-        if any(int((row == IMAGE_TOKEN_INDEX).sum()) > 1 for row in ids_cpu):
-            raise NotImplementedError("exactly one image per sample (train_fsdp.py:1100)")
-        needs_expand = False
-        for row in ids_cpu:
-            pos = torch.where(row == IMAGE_TOKEN_INDEX)[0]
-            if len(pos) == 1:
-                p0 = int(pos[0])
-                if p0 + span > row.shape[0] or bool((row[p0 + 1:p0 + span] != 0).any()):
-                    needs_expand = True
-        if needs_expand:
-            input_ids, labels, attention_mask, position_ids = _expand_image_tokens(
-                ids_cpu, labels, attention_mask, span, input_ids.device)
+        if image_positions is not None:
+            starts = [int(p) for p in image_positions]
+        else:
             ids_cpu = input_ids.detach().to("cpu")
-        starts = []
-        for row in ids_cpu:
-            pos = torch.where(row == IMAGE_TOKEN_INDEX)[0]
-            starts.append(int(pos[0]) if len(pos) else -1)
-        img_start = torch.tensor(starts, dtype=torch.int32, device=input_ids.device)
+            if any(int((row == IMAGE_TOKEN_INDEX).sum()) > 1 for row in ids_cpu):
+                raise NotImplementedError("exactly one image per sample (train_fsdp.py:1100)")
+            needs_expand = False
+            for row in ids_cpu:
+                pos = torch.where(row == IMAGE_TOKEN_INDEX)[0]
+                if len(pos) == 1:
+                    p0 = int(pos[0])
+                    if p0 + span > row.shape[0] or bool((row[p0 + 1:p0 + span] != 0).any()):
+                        needs_expand = True
+            if needs_expand:
+                input_ids, labels, attention_mask, position_ids = _expand_image_tokens(
+                    ids_cpu, labels, attention_mask, span, input_ids.device)
+                ids_cpu = input_ids.detach().to("cpu")
+            starts = []
+            for row in ids_cpu:
+                pos = torch.where(row == IMAGE_TOKEN_INDEX)[0]
+                starts.append(int(pos[0]) if len(pos) else -1)
+        img_start = torch.tensor(starts, dtype=torch.int32).to(input_ids.device, non_blocking=True)
 
         feats = self.encode_images(images)                                                      # :366
         feats_final = masks_final = ctx_final = None

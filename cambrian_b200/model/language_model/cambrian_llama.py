@@ -355,15 +355,17 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
                 output_hidden_states: Optional[bool] = None, images: Optional[List[torch.Tensor]] = None,
                 image_aux_attention_masks_list: Optional[List[torch.Tensor]] = None,
                 image_sizes: Optional[List[List[int]]] = None, return_dict: Optional[bool] = None,
-                cache_position=None, num_valid_labels: Optional[int] = None, **kw):
-        """cambrian_llama.py:297-434.  Extension: `num_valid_labels` (host int, number of non-ignored shifted labels)
-        avoids a device->host sync when the collator already knows it."""
+                cache_position=None, num_valid_labels: Optional[int] = None,
+                image_positions: Optional[List[int]] = None, **kw):
+        """cambrian_llama.py:297-434.  Extensions (host-side hints the collator already has; both avoid a device->host
+        sync per step): `num_valid_labels` = number of non-ignored shifted labels, `image_positions` = index of the
+        <image> indicator per sample of an already-expanded batch."""
         feats = masks = final_size = ctx_feat = None
         if inputs_embeds is None:
             (input_ids, position_ids, attention_mask, past_key_values, inputs_embeds, labels, feats, masks, final_size,
              ctx_feat) = self.prepare_inputs_labels_for_multimodal(
                 input_ids, position_ids, attention_mask, past_key_values, labels, images, image_aux_attention_masks_list,
-                image_sizes)
+                image_sizes, image_positions=image_positions)
         out = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
                          past_key_values=past_key_values, inputs_embeds=inputs_embeds, use_cache=use_cache,
                          output_attentions=output_attentions, output_hidden_states=output_hidden_states, return_dict=True,
