@@ -308,7 +308,7 @@ class DecoderLayerFn(torch.autograd.Function):
         act = ops.swiglu_fwd(gu[:, :I], gu[:, I:])
         out = ops.gemm(act, down_w, residual=x1)
         if keep:
-            return out.view(B, S, H), (rstd1, qkv, attn, lse, x1, rstd2, gu)
+            return out.view(B, S, H), (rstd1, qkv, attn, lse, x1, rstd2, gu, act)
         return out.view(B, S, H), None
 
     @staticmethod
@@ -334,7 +334,7 @@ class DecoderLayerFn(torch.autograd.Function):
             _, saved = DecoderLayerFn._forward(meta, x, ln1, qkv_w, o_w, ln2, gu_w, down_w, True)
         else:
             saved = sv[7:]
-        rstd1, qkv, attn, lse, x1, rstd2, gu = saved
+        rstd1, qkv, attn, lse, x1, rstd2, gu, act = saved
         # p_qkv / p_gu: holders exposing .main_grad (fused view over the three / two adjacent grad slices) or None
         p_ln1, p_qkv, p_o, p_ln2, p_gu, p_down = meta["params"]
         B, S, H = x.shape
@@ -345,7 +345,6 @@ class DecoderLayerFn(torch.autograd.Function):
         dx2 = dout.reshape(rows, H).contiguous()
         # ---- MLP
         h2 = ops.rmsnorm_fwd(x1, ln2, meta["eps"], meta["hf_cast"])       # cheap recompute (bandwidth only)
-        act = ops.swiglu_fwd(gu[:, :I], gu[:, I:])
         dact = ops.gemm(dx2, down_w, b_mn=True)
         g_down = wgrad(p_down, dx2, act)
         del act

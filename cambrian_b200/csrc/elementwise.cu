@@ -326,37 +326,74 @@ __global__ void patchify_nhwc_kernel(const bf16* __restrict__ in, bf16* __restri
 // y[b,y,x,c] = bias[c] + sum_{dy,dx} w[dy,dx,c] * x[b, y+dy-3, x+dx-3, c]     (timm ConvNeXtBlock.conv_dw,
 // reached from clip_convnext_encoder.py:121-144).  Weights pre-permuted to [7,7,C].  Each thread owns 8 channels
 // of one output pixel; neighbouring threads share input rows through L1/L2 (bandwidth-bound, 49 taps).
-__global__ void dwconv7_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const bf16* __restrict__ bias,
-                               bf16* __restrict__ out, int B, int H, int W, int C) {
+// Register-tiled version: each thread owns 8 channels of a 2 x 4 patch of output pixels and walks the 8 input rows the
+// patch needs once (10 input vectors per row), so every loaded input vector feeds up to 2 x 7 taps instead of one —
+// 22 vector loads per output instead of 98 (the first, one-output-per-thread version was 5.3% of the training step).
+constexpr int DW_TY = 2, DW_TX = 4;
+__global__ void __launch_bounds__(128)
+dwconv7_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const bf16* __restrict__ bias,
+               bf16* __restrict__ out, int B, int H, int W, int C) {
   const int vpr = C >> 3;
-  const long long total = (long long)B * H * W * vpr;
+  const int txn = (W + DW_TX - 1) / DW_TX, tyn = (H + DW_TY - 1) / DW_TY;
+  const long long total = (long long)B * tyn * txn * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % vpr);
     long long t = i / vpr;
-    const int x = (int)(t % W);
-    t /= W;
-    const int y = (int)(t % H);
-    const int b = (int)(t / H);
-    float acc[8];
-    if (bias) unpack8(reinterpret_cast<const uint4*>(bias)[v], acc);
-    else {
+    const int tx = (int)(t % txn);
+    t /= txn;
+    const int ty = (int)(t % tyn);
+    const int b = (int)(t / tyn);
+    const int x0 = tx * DW_TX, y0 = ty * DW_TY;
+    float acc[DW_TY][DW_TX][8];
+    {
+      float bv[8];
+      if (bias) unpack8(reinterpret_cast<const uint4*>(bias)[v], bv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      for (int oy = 0; oy < DW_TY; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < DW_TX; ++ox)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[oy][ox][e] = bias ? bv[e] : 0.f;
     }
-    for (int dy = 0; dy < 7; ++dy) {
-      const int yy = y + dy - 3;
-      if (yy < 0 || yy >= H) continue;
-      for (int dx = 0; dx < 7; ++dx) {
-        const int xx = x + dx - 3;
-        if (xx < 0 || xx >= W) continue;
-        float a[8], k[8];
-        unpack8(*(reinterpret_cast<const uint4*>(in + (((long long)b * H + yy) * W + xx) * C) + v), a);
-        unpack8(reinterpret_cast<const uint4*>(w + (long long)(dy * 7 + dx) * C)[v], k);
+    const bf16* img = in + (long long)b * H * W * C + v * 8;
+#pragma unroll 1
+    for (int r = 0; r < DW_TY + 6; ++r) {
+      const int iy = y0 + r - 3;
+      if (iy < 0 || iy >= H) continue;
+      float row[DW_TX + 6][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += a[e] * k[e];
+      for (int c = 0; c < DW_TX + 6; ++c) {
+        const int ix = x0 + c - 3;
+        if (ix >= 0 && ix < W) {
+          unpack8(*reinterpret_cast<const uint4*>(img + ((long long)iy * W + ix) * C), row[c]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) row[c][e] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int oy = 0; oy < DW_TY; ++oy) {
+        const int ky = r - oy;
+        if (ky < 0 || ky > 6) continue;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          float k[8];
+          unpack8(reinterpret_cast<const uint4*>(w + (long long)(ky * 7 + kx) * C)[v], k);
+#pragma unroll
+          for (int ox = 0; ox < DW_TX; ++ox)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[oy][ox][e] = fmaf(row[ox + kx][e], k[e], acc[oy][ox][e]);
+        }
       }
     }
-    reinterpret_cast<uint4*>(out)[i] = pack8(acc);
+#pragma unroll
+    for (int oy = 0; oy < DW_TY; ++oy)
+#pragma unroll
+      for (int ox = 0; ox < DW_TX; ++ox) {
+        const int y = y0 + oy, x = x0 + ox;
+        if (y < H && x < W)
+          *reinterpret_cast<uint4*>(out + (((long long)b * H + y) * W + x) * C + v * 8) = pack8(acc[oy][ox]);
+      }
   }
 }
 
@@ -706,7 +743,7 @@ int patchify_nhwc_launch(const void* in, void* out, int B, int H, int W, int C, 
 int dwconv7_launch(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int C,
                    cudaStream_t st) {
   VEC_CHECK(C, "dwconv7");
-  dwconv7_kernel<<<grid_for((long long)B * H * W * (C / 8), 128, 16), 128, 0, st>>>((const bf16*)in, (const bf16*)w,
+  dwconv7_kernel<<<grid_for((long long)B * ((H + DW_TY - 1) / DW_TY) * ((W + DW_TX - 1) / DW_TX) * (C / 8), 128, 16), 128, 0, st>>>((const bf16*)in, (const bf16*)w,
                                                                                    (const bf16*)bias, (bf16*)out, B, H, W, C);
   CB_CUDA_LAUNCH_CHECK("dwconv7");
   return CB_OK;

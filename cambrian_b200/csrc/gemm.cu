@@ -9,10 +9,12 @@
 //     a_mn = 0 : A stored [M, K] (K contiguous)       a_mn = 1 : A stored [K, M] (M contiguous)
 //     b_mn = 0 : B stored [N, K] (nn.Linear weight)   b_mn = 1 : B stored [K, N] (N contiguous)
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM, 320 threads):
 //     warp 0      TMA producer   : cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx
 //     warp 1      MMA issuer     : one lane issues tcgen05.mma 128 x BN x 16, accumulators in TMEM
-//     warps 2..5  epilogue       : tcgen05.ld TMEM -> regs -> bias / act / scale / residual -> HBM
+//     warps 2..9  epilogue       : tcgen05.ld TMEM -> regs -> bias / act / scale / residual -> HBM
+//                                  (two warps per TMEM lane quarter, each owning half of the tile's columns, so an
+//                                   activation-heavy epilogue such as GELU keeps up with short-K mainloops)
 // The TMEM accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include <cudaTypedefs.h>
@@ -58,7 +60,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   int M, int N, int K, int batch, GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
@@ -92,7 +94,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 8);  // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -180,7 +182,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ============================ epilogue ================================
-    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are owned by this warp
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    const int col_half = (warp - 2) >> 2;  // warps 2-5: first half of the tile's columns, warps 6-9: second half
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -197,7 +200,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const long long c_off = static_cast<long long>(b) * ep.bsc + static_cast<long long>(row) * ep.ldc;
       const long long r_off = static_cast<long long>(b) * ep.bsr + static_cast<long long>(row) * ep.ldr;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = col_half * (BN / 64); c < (col_half + 1) * (BN / 64); ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= N) break;  // warp-uniform
         uint32_t rr[32];
@@ -339,7 +342,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * batch;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, batch, ep);
+  kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, batch, ep);
   CB_CUDA_LAUNCH_CHECK("gemm_bf16_tcgen05");
   return CB_OK;
 }

@@ -126,7 +126,7 @@ norm_fwd_kernel(const bf16* __restrict__ X, const bf16* __restrict__ gamma, cons
 }
 
 // backward: dx per row; per-block partial sums of dgamma / dbeta into part_g / part_b [P, C] (fp32)
-template <int TPR, bool RMS>
+template <int TPR, bool RMS, int VPT>
 __global__ void __launch_bounds__(TPR < 256 ? 256 : TPR)
 norm_bwd_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, const bf16* __restrict__ gamma,
                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, bf16* __restrict__ dX,
@@ -136,10 +136,10 @@ norm_bwd_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, const b
   __shared__ float red[RPB * (TPR / 32) + 1];
   const int slot = threadIdx.x / TPR, tir = threadIdx.x % TPR;
   const int nvec = C >> 3;
-  float g[NORM_VPT][8], ag[NORM_VPT][8], ab[NORM_VPT][8];
+  float g[VPT][8], ag[VPT][8], ab[VPT][8];
   const uint4* gp = reinterpret_cast<const uint4*>(gamma);
 #pragma unroll
-  for (int i = 0; i < NORM_VPT; ++i) {
+  for (int i = 0; i < VPT; ++i) {
     const int vi = tir + i * TPR;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { ag[i][e] = 0.f; ab[i][e] = 0.f; g[i][e] = 0.f; }
@@ -150,7 +150,7 @@ norm_bwd_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, const b
   for (long long it = 0; it < iters; ++it) {
     const long long row = it * row_stride + (long long)blockIdx.x * RPB + slot;
     const bool active = row < rows;
-    float x[NORM_VPT][8], dy[NORM_VPT][8];
+    float x[VPT][8], dy[VPT][8];
     const float mean = (!RMS && active) ? mean_in[row] : 0.f;
     const float rstd = active ? rstd_in[row] : 0.f;
     const uint4* xp = reinterpret_cast<const uint4*>(X + (active ? row : 0) * C);
@@ -159,7 +159,7 @@ norm_bwd_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, const b
     if (pa.pos && active) pp = reinterpret_cast<const uint4*>(pa.pos + (size_t)pos_index(pa, row) * C);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_VPT; ++i) {
+    for (int i = 0; i < VPT; ++i) {
       const int vi = tir + i * TPR;
       if (active && vi < nvec) {
         unpack8(ldg_nc(xp + vi), x[i]);
@@ -188,7 +188,7 @@ norm_bwd_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, const b
     if (active) {
       uint4* dxp = reinterpret_cast<uint4*>(dX + row * C);
 #pragma unroll
-      for (int i = 0; i < NORM_VPT; ++i) {
+      for (int i = 0; i < VPT; ++i) {
         const int vi = tir + i * TPR;
         if (vi < nvec) {
           float o[8];
@@ -208,7 +208,7 @@ norm_bwd_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, const b
   }
   const size_t prow = (size_t)blockIdx.x * RPB + slot;
 #pragma unroll
-  for (int i = 0; i < NORM_VPT; ++i) {
+  for (int i = 0; i < VPT; ++i) {
     const int vi = tir + i * TPR;
     if (vi < nvec) {
       float4* pg = reinterpret_cast<float4*>(part_g + prow * C + (size_t)vi * 8);
@@ -224,18 +224,30 @@ norm_bwd_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, const b
 }
 
 // out[c] = sum_p part[p, c]  (deterministic fixed-order column reduction)
-__global__ void colsum_kernel(const float* __restrict__ part, int P, int C, bf16* __restrict__ out_bf16,
-                              float* __restrict__ out_f32) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// 32 columns x 32 row-lanes per block: coalesced 128 B reads, fixed-order (deterministic) tree over the row lanes.
+// (The first version used one thread per column over all P partial rows: 16 blocks for C = 4096 -> 135 us per call,
+//  7.5% of the whole training step in the r01 launch list.)
+__global__ void __launch_bounds__(1024)
+colsum_kernel(const float* __restrict__ part, int P, int C, bf16* __restrict__ out_bf16, float* __restrict__ out_f32) {
+  __shared__ float red[32][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int p = 0; p < P; ++p) s += part[(size_t)p * C + c];
-  if (out_bf16) out_bf16[c] = __float2bfloat16(s);
-  if (out_f32) out_f32[c] = s;
+  if (c < C)
+    for (int p = ry; p < P; p += 32) s += part[(size_t)p * C + c];
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += red[k][cx];
+    if (out_bf16) out_bf16[c] = __float2bfloat16(t);
+    if (out_f32) out_f32[c] = t;
+  }
 }
 
-static int pick_tpr(int C) {
-  const int need = (C / 8 + NORM_VPT - 1) / NORM_VPT;
+static int pick_tpr(int C, int vpt = NORM_VPT) {
+  const int need = (C / 8 + vpt - 1) / vpt;
   if (need <= 32) return 32;
   if (need <= 64) return 64;
   if (need <= 128) return 128;
@@ -271,11 +283,19 @@ static int norm_fwd_t(const void* x, const void* gamma, const void* beta, void* 
   return CB_OK;
 }
 
+// backward keeps x_hat, gamma*dy and two partial-sum arrays live: 2 vectors per thread (instead of 4) halves the
+// register footprint (196 -> ~110) so 2-3 blocks fit per SM; rows wider than 512*2 vectors fall back to 4.
+static void bwd_cfg(int C, int* tpr, int* vpt) {
+  *vpt = (C / 8 <= 1024) ? 2 : 4;
+  *tpr = pick_tpr(C, *vpt);
+}
+
 template <bool RMS>
 static int norm_bwd_t(const void* dy, const void* x, const void* gamma, const float* mean, const float* rstd,
                       void* dx, const void* dres, void* dgamma, void* dbeta, float* workspace, long long ws_floats,
                       long long rows, int C, PosAdd pa, cudaStream_t st) {
-  const int tpr = pick_tpr(C);
+  int tpr, vpt;
+  bwd_cfg(C, &tpr, &vpt);
   CB_CHECK_ARG(C % 8 == 0 && tpr != 0, "norm bwd: C=%d must be a multiple of 8 and <= 16384", C);
   CB_CHECK_ARG(rows > 0, "norm bwd: rows=%lld", rows);
   const int rpb = tpr < 256 ? 256 / tpr : 1;
@@ -287,21 +307,25 @@ static int norm_bwd_t(const void* dy, const void* x, const void* gamma, const fl
                ws_floats, 2 * P * C);
   float* part_g = workspace;
   float* part_b = workspace + P * C;
-#define CB_NORM_BWD(T)                                                                                  \
-  norm_bwd_kernel<T, RMS><<<(unsigned)grid, T < 256 ? 256 : T, 0, st>>>(                               \
+#define CB_NORM_BWD(T, V)                                                                                   \
+  norm_bwd_kernel<T, RMS, V><<<(unsigned)grid, T < 256 ? 256 : T, 0, st>>>(                                \
       (const bf16*)dy, (const bf16*)x, (const bf16*)gamma, mean, rstd, (bf16*)dx, (const bf16*)dres, part_g, part_b, \
       rows, C, pa);
-  switch (tpr) {
-    case 32: CB_NORM_BWD(32) break;
-    case 64: CB_NORM_BWD(64) break;
-    case 128: CB_NORM_BWD(128) break;
-    case 256: CB_NORM_BWD(256) break;
-    default: CB_NORM_BWD(512) break;
+  if (vpt == 2) {
+    switch (tpr) {
+      case 32: CB_NORM_BWD(32, 2) break;
+      case 64: CB_NORM_BWD(64, 2) break;
+      case 128: CB_NORM_BWD(128, 2) break;
+      case 256: CB_NORM_BWD(256, 2) break;
+      default: CB_NORM_BWD(512, 2) break;
+    }
+  } else {
+    CB_NORM_BWD(512, 4)
   }
 #undef CB_NORM_BWD
   CB_CUDA_LAUNCH_CHECK("norm_bwd");
-  colsum_kernel<<<(C + 255) / 256, 256, 0, st>>>(part_g, (int)P, C, (bf16*)dgamma, nullptr);
-  if (!RMS && dbeta) colsum_kernel<<<(C + 255) / 256, 256, 0, st>>>(part_b, (int)P, C, (bf16*)dbeta, nullptr);
+  colsum_kernel<<<(C + 31) / 32, 1024, 0, st>>>(part_g, (int)P, C, (bf16*)dgamma, nullptr);
+  if (!RMS && dbeta) colsum_kernel<<<(C + 31) / 32, 1024, 0, st>>>(part_b, (int)P, C, (bf16*)dbeta, nullptr);
   CB_CUDA_LAUNCH_CHECK("norm_bwd colsum");
   return CB_OK;
 }
@@ -328,7 +352,8 @@ int rmsnorm_bwd(const void* dy, const void* x, const void* gamma, const float* r
   return norm_bwd_t<true>(dy, x, gamma, nullptr, rstd, dx, dres, dgamma, nullptr, ws, ws_floats, rows, C, pa, st);
 }
 long long norm_bwd_workspace_floats(long long rows, int C) {
-  const int tpr = pick_tpr(C);
+  int tpr, vpt;
+  bwd_cfg(C, &tpr, &vpt);
   if (!tpr) return 0;
   const int rpb = tpr < 256 ? 256 / tpr : 1;
   long long grid = (rows + rpb - 1) / rpb;
