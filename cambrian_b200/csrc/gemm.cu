@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace cb {
 
@@ -56,6 +57,83 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case 3: return quick_gelu(v);
     case 4: return silu(v);
     default: return v;
+  }
+}
+
+// Epilogue of one accumulator tile for the 32-column chunks [c_begin, c_end) owned by this warp:
+// tcgen05.ld -> alpha, bias, activation, LayerScale, residual, accumulate -> bf16 / fp32 stores.
+template <int BN>
+__device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_t taddr, int row, bool row_ok, int b,
+                                                 int n0, int N, int c_begin, int c_end) {
+  const long long c_off = static_cast<long long>(b) * ep.bsc + static_cast<long long>(row) * ep.ldc;
+  const long long r_off = static_cast<long long>(b) * ep.bsr + static_cast<long long>(row) * ep.ldr;
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= N) break;  // warp-uniform
+    uint32_t rr[32];
+    tmem_ld32(taddr + c * 32, rr);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = col0 + g * 8;
+        if (col >= N) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[g * 8 + j]) * ep.alpha;
+        const int nvalid = min(8, N - col);
+        if (ep.bias) {
+          for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(ep.bias[col + j]);
+        }
+        if (ep.act) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
+        }
+        if (ep.colscale) {
+          for (int j = 0; j < nvalid; ++j) v[j] *= __bfloat162float(ep.colscale[col + j]);
+        }
+        if (ep.residual) {
+          if (ep.vec_ok) {
+            float t[8];
+            unpack8(*reinterpret_cast<const uint4*>(ep.residual + r_off + col), t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += t[j];
+          } else {
+            for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(ep.residual[r_off + col + j]);
+          }
+        }
+        if (ep.out_fp32) {
+          float* cp = reinterpret_cast<float*>(ep.C) + c_off + col;
+          if (ep.vec_ok) {
+            float4* c4 = reinterpret_cast<float4*>(cp);
+            if (ep.accumulate) {
+              const float4 o0 = c4[0], o1 = c4[1];
+              v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
+              v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+            }
+            c4[0] = make_float4(v[0], v[1], v[2], v[3]);
+            c4[1] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            for (int j = 0; j < nvalid; ++j) cp[j] = ep.accumulate ? cp[j] + v[j] : v[j];
+          }
+        } else {
+          bf16* cp = reinterpret_cast<bf16*>(ep.C) + c_off + col;
+          if (ep.vec_ok) {
+            if (ep.accumulate) {
+              float t[8];
+              unpack8(*reinterpret_cast<const uint4*>(cp), t);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += t[j];
+            }
+            *reinterpret_cast<uint4*>(cp) = pack8(v);
+          } else {
+            for (int j = 0; j < nvalid; ++j)
+              cp[j] = __float2bfloat16(ep.accumulate ? __bfloat162float(cp[j]) + v[j] : v[j]);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -197,76 +275,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
-      const long long c_off = static_cast<long long>(b) * ep.bsc + static_cast<long long>(row) * ep.ldc;
-      const long long r_off = static_cast<long long>(b) * ep.bsr + static_cast<long long>(row) * ep.ldr;
-#pragma unroll 1
-      for (int c = col_half * (BN / 64); c < (col_half + 1) * (BN / 64); ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= N) break;  // warp-uniform
-        uint32_t rr[32];
-        tmem_ld32(taddr + c * 32, rr);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col >= N) break;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[g * 8 + j]) * ep.alpha;
-            const int nvalid = min(8, N - col);
-            if (ep.bias) {
-              for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(ep.bias[col + j]);
-            }
-            if (ep.act) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
-            }
-            if (ep.colscale) {
-              for (int j = 0; j < nvalid; ++j) v[j] *= __bfloat162float(ep.colscale[col + j]);
-            }
-            if (ep.residual) {
-              if (ep.vec_ok) {
-                float t[8];
-                unpack8(*reinterpret_cast<const uint4*>(ep.residual + r_off + col), t);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += t[j];
-              } else {
-                for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(ep.residual[r_off + col + j]);
-              }
-            }
-            if (ep.out_fp32) {
-              float* cp = reinterpret_cast<float*>(ep.C) + c_off + col;
-              if (ep.vec_ok) {
-                float4* c4 = reinterpret_cast<float4*>(cp);
-                if (ep.accumulate) {
-                  const float4 o0 = c4[0], o1 = c4[1];
-                  v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
-                  v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
-                }
-                c4[0] = make_float4(v[0], v[1], v[2], v[3]);
-                c4[1] = make_float4(v[4], v[5], v[6], v[7]);
-              } else {
-                for (int j = 0; j < nvalid; ++j) cp[j] = ep.accumulate ? cp[j] + v[j] : v[j];
-              }
-            } else {
-              bf16* cp = reinterpret_cast<bf16*>(ep.C) + c_off + col;
-              if (ep.vec_ok) {
-                if (ep.accumulate) {
-                  float t[8];
-                  unpack8(*reinterpret_cast<const uint4*>(cp), t);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] += t[j];
-                }
-                *reinterpret_cast<uint4*>(cp) = pack8(v);
-              } else {
-                for (int j = 0; j < nvalid; ++j)
-                  cp[j] = __float2bfloat16(ep.accumulate ? __bfloat162float(cp[j]) + v[j] : v[j]);
-              }
-            }
-          }
-        }
-      }
+      epilogue_columns<BN>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64), (col_half + 1) * (BN / 64));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -281,6 +290,182 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a (2,1,1) cluster computes one 256 x BN tile.  Each CTA stages its own 128 rows of
+// A and HALF of the B tile (BN/2 rows), so the operand bytes streamed into and read out of each SM's shared memory per
+// FLOP drop by a third versus the 128 x BN single-CTA tile — the shared-memory port, not the tensor pipe, bounds the
+// single-CTA kernel at ~65% utilisation under the power cap.  The leader CTA's MMA warp issues tcgen05.mma.cta_group::2
+// (M = 256); both CTAs' TMA loads credit the leader's `full` barrier; tcgen05.commit multicasts to both CTAs' `empty` /
+// `tmem_full` barriers; both CTAs' epilogue warps arrive on the leader's `tmem_empty` barrier.
+// ------------------------------------------------------------------------------------------
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int HALF_N = BN / 2;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = HALF_N * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                       int K, int batch, GemmEpilogue ep) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int m_blocks = (M + 2 * BM - 1) / (2 * BM);
+  const int n_blocks = (N + BN - 1) / BN;
+  const int tiles_per_batch = m_blocks * n_blocks;
+  const int num_tiles = tiles_per_batch * batch;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);   // leader's copy is the one in use: its own arrive.expect_tx, bytes from both CTAs
+      mbar_init(empty_bar(s), 1);  // multicast commit from the leader's MMA thread
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 16);  // 8 epilogue warps x 2 CTAs arrive on the leader's copy
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation of both CTAs visible before any cross-CTA traffic
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ============================ TMA producer (both CTAs) ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int b = tile / tiles_per_batch;
+        const int r = tile - b * tiles_per_batch;
+        const int m0 = (r % m_blocks) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (r / m_blocks) * BN + static_cast<int>(rank) * Cfg::HALF_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_3d_2cta(sa, &tmA, full_bar(stage), k0, m0, b);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_3d_2cta(sa + i * (64 * BK * 2), &tmA, full_bar(stage), m0 + 64 * i, k0, b);
+          }
+          if (!B_MN) {
+            tma_load_3d_2cta(sb, &tmB, full_bar(stage), k0, n0, b);
+          } else {
+#pragma unroll
+            for (int i = 0; i < Cfg::HALF_N / 64; ++i)
+              tma_load_3d_2cta(sb + i * (64 * BK * 2), &tmB, full_bar(stage), n0 + 64 * i, k0, b);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (leader CTA only) ========================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(sa + k * 2048, 64 * BK * 2, 1024)
+                                        : make_smem_desc_sw128(sa + k * 32, 0, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024)
+                                        : make_smem_desc_sw128(sb + k * 32, 0, 1024);
+            umma_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit_2cta_mc(empty_bar(stage), 3);  // frees the slot in BOTH CTAs
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit_2cta_mc(tfull_bar(acc), 3);  // accumulator halves complete in both CTAs' TMEM
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ============================ epilogue (both CTAs, own 128 rows) ==================
+    const int lane_grp = warp & 3;
+    const int col_half = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int b = tile / tiles_per_batch;
+      const int r = tile - b * tiles_per_batch;
+      const int m0 = (r % m_blocks) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (r / m_blocks) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + lane_grp * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
+                             static_cast<uint32_t>(acc * BN);
+      epilogue_columns<BN>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64), (col_half + 1) * (BN / 64));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // leader's barrier
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the leader's MMAs read the peer's smem: nobody may exit (or free TMEM) before both are done
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -347,6 +532,43 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   return CB_OK;
 }
 
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int batch,
+                        const GemmEpilogue& ep, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  auto kern = gemm_bf16_tcgen05_2cta<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(CB_ERR_CUDA, "gemm2 smem attr: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN) * batch;
+  const int pairs = device_sm_count() / 2;
+  const int clusters = tiles < pairs ? tiles : pairs;
+  kern<<<2 * clusters, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, batch, ep);
+  CB_CUDA_LAUNCH_CHECK("gemm_bf16_tcgen05_2cta");
+  return CB_OK;
+}
+
+static int dispatch_2cta(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+                         int batch, const GemmEpilogue& ep, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm2<256, false, false>(tmA, tmB, M, N, K, batch, ep, stream);
+  if (!a_mn && b_mn) return launch_gemm2<256, false, true>(tmA, tmB, M, N, K, batch, ep, stream);
+  if (a_mn && !b_mn) return launch_gemm2<256, true, false>(tmA, tmB, M, N, K, batch, ep, stream);
+  return launch_gemm2<256, true, true>(tmA, tmB, M, N, K, batch, ep, stream);
+}
+
+// CB_GEMM_2CTA=0 disables the CTA-pair kernel (read once)
+static bool two_cta_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CB_GEMM_2CTA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int BN>
 static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N,
                           int K, int batch, const GemmEpilogue& ep, cudaStream_t stream) {
@@ -367,6 +589,14 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
   CUtensorMap tmA, tmB;
   int rc;
   int bn = force_bn;
+  // force_bn = 512 selects the CTA-pair (256 x 256 per cluster) kernel explicitly; the heuristic picks it for problems
+  // that fill the 74 SM pairs for at least ~3 waves (the large decoder / lm_head / ConvNeXt GEMMs)
+  bool use_2cta = (force_bn == 512);
+  if (force_bn == 0 && two_cta_enabled() && N >= 256) {
+    const long long t2 = (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256) * batch;
+    if (t2 >= 3LL * (device_sm_count() / 2)) use_2cta = true;
+  }
+  if (use_2cta) bn = 256;
   if (bn == 0) {
     const int sms = device_sm_count();
     const long long mb = (M + BM - 1) / BM;
@@ -380,7 +610,7 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
   if (!a_mn) rc = make_tmap_bf16_3d(&tmA, A, K, M, batch, lda, bsa, BM);
   else       rc = make_tmap_bf16_3d(&tmA, A, M, K, batch, lda, bsa, BK);
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap_bf16_3d(&tmB, B, K, N, batch, ldb, bsb, bn);
+  if (!b_mn) rc = make_tmap_bf16_3d(&tmB, B, K, N, batch, ldb, bsb, use_2cta ? bn / 2 : bn);
   else       rc = make_tmap_bf16_3d(&tmB, B, N, K, batch, ldb, bsb, BK);
   if (rc) return rc;
   GemmEpilogue ep;
@@ -396,6 +626,7 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
   if (residual)
     vec = vec && (ldr % 8 == 0) && (bsr % 8 == 0) && ((reinterpret_cast<uintptr_t>(residual) & 15u) == 0);
   ep.vec_ok = vec ? 1 : 0;
+  if (use_2cta) return dispatch_2cta(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
   switch (bn) {
     case 256: return dispatch_major<256>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
     case 128: return dispatch_major<128>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);

@@ -99,6 +99,32 @@ def group_gemm_epi():
     gemm_case(77, 50, 64, False, False, 0, bias=True, residual=True)  # scalar (non-vector) store path
 
 
+def group_gemm_2cta():
+    """CTA-pair kernel (force_bn=512): all operand layouts, tails, epilogues, then throughput vs the single-CTA kernel."""
+    for a_mn in (False, True):
+        for b_mn in (False, True):
+            gemm_case(512, 512, 256, a_mn, b_mn, 512, fp32=True)
+    for (M, N, K) in [(256, 256, 64), (1000, 768, 520), (2304, 1024, 2048), (4096, 4096, 4096), (300, 520, 72)]:
+        for a_mn, b_mn in ((False, False), (False, True), (True, False), (True, True)):
+            if (a_mn and M % 8) or (b_mn and N % 8):
+                continue
+            gemm_case(M, N, K, a_mn, b_mn, 512, fp32=True)
+    gemm_case(512, 768, 512, False, False, 512, batch=3, fp32=True)
+    gemm_case(512, 1024, 512, False, False, 512, bias=True, act="gelu", residual=True)
+    gemm_case(512, 1024, 512, True, True, 512, accumulate=True)
+    for (M, N, K) in [(8192, 8192, 8192), (8192, 28672, 4096), (8192, 4096, 14336), (8192, 6144, 4096)]:
+        for a_mn, b_mn in ((False, False), (False, True), (True, True)):
+            a = torch.randn((K, M) if a_mn else (M, K), device=dev).bfloat16()
+            b = torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16()
+            out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            for bn in (256, 512):
+                ms = timeit(lambda: ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out=out, force_bn=bn))
+                print(f"perf gemm M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} bn={bn}: {ms:.4f} ms "
+                      f"{2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+        ms = timeit(lambda: torch.matmul(a if not a_mn else a.t(), (b.t() if not b_mn else b), out=out))
+        print(f"perf cublas M={M} N={N} K={K}: {ms:.4f} ms {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
 def group_gemm_perf():
     for (M, N, K) in [(8192, 8192, 8192), (8192, 14336, 4096), (8192, 4096, 14336), (4096, 4096, 4096),
                       (2304, 1024, 1024)]:
