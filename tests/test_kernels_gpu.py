@@ -33,6 +33,10 @@ def test_gemm_epilogues(capsys):
     _run("probe1", "gemm_epi", capsys, 10)
 
 
+def test_gemm_cta_pair_kernel(capsys):
+    _run("probe1", "gemm_2cta", capsys, 30)
+
+
 def test_sva_window_attention_fwd_bwd(capsys):
     _run("probe1", "sva", capsys, 4)
 
