@@ -16,6 +16,14 @@ import torch
 from . import ops
 
 
+def _notify(param):
+    """Tell the TrainEngine (if any) that one gradient contribution of `param` has been enqueued on the stream; it uses
+    the per-step contribution counts to launch a bucket's all-reduce as soon as the bucket is final."""
+    n = getattr(param, "_cb_notify", None)
+    if n is not None:
+        n()
+
+
 def wgrad(param: torch.Tensor, dy2d: torch.Tensor, x2d: torch.Tensor, out_view=None):
     """dW[N_out, K_in] = dy2d[rows, N_out]^T @ x2d[rows, K_in].  `out_view` selects a column slice of the gradient
     (used for proj_in's two halves)."""
@@ -28,6 +36,7 @@ def wgrad(param: torch.Tensor, dy2d: torch.Tensor, x2d: torch.Tensor, out_view=N
         ops.gemm(dy2d, x2d, a_mn=True, b_mn=True, out=tgt, accumulate=not first)
         if fresh is not None:
             fresh.add(key)
+        _notify(param)
         return None
     return ops.gemm(dy2d, x2d, a_mn=True, b_mn=True)
 
@@ -42,6 +51,7 @@ def vgrad(param: torch.Tensor, g: torch.Tensor):
             fresh.add("all")
         else:
             ops.add_(mg.view(-1), g.contiguous().view(-1)) if mg.numel() % 8 == 0 else mg.add_(g.view_as(mg))
+        _notify(param)
         return None
     return g
 
@@ -415,6 +425,8 @@ class EmbedSpliceFn(torch.autograd.Function):
                 tgt = torch.zeros(ctx.vshape, dtype=torch.bfloat16, device=dout.device)
                 d_embed_ret = tgt
         d_img, d_nl_rows = ops.embed_splice_bwd(dout, meta["ids"], meta["img_start"], tgt, meta["q_side"], ctx.has_img)
+        if tgt is not None and d_embed_ret is None:
+            _notify(p_embed)
         d_nl = None
         if ctx.has_img and ctx.needs_input_grad[3]:
             d_nl = vgrad(p_newline, ops.group_colsum(d_nl_rows, 1).view(-1))

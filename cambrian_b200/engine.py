@@ -5,15 +5,19 @@ buffers for bf16 gradients, fp32 master weights and fp32 Adam moments:
 
   * weight-gradient GEMMs accumulate straight into `param.main_grad` (a view of the flat gradient buffer), so
     autograd never materialises or sums parameter gradients;
-  * gradient reduction = NCCL all-reduce over contiguous buckets of the flat gradient buffer, launched as soon as the
-    last parameter of a bucket has its gradient written (backward runs last-layer-first, buckets are laid out in the
-    same order), overlapping NVLink traffic with the remaining backward GEMMs; frozen towers are never reduced;
-  * the optimizer is one fused AdamW kernel over the flat buffers (fp32 master update -> bf16 compute copy).
+  * gradient reduction = NCCL all-reduce over contiguous buckets of the flat gradient buffer.  Each parameter's number
+    of gradient contributions per step is learned on the first step; from then on a bucket's all-reduce is launched
+    (asynchronously, on NCCL's stream) the moment its last contribution has been enqueued, so NVLink traffic overlaps
+    the remaining backward GEMMs.  Frozen towers are never reduced;
+  * the optimizer is one fused AdamW kernel over the flat buffers (fp32 master update -> bf16 compute copy), with the
+    1/world gradient average folded in.
 
 The reference does its gradient reduction inside torch_xla FSDP (`xm.all_reduce` helper at
 cambrian_trainer.py:181-190) and steps HF Trainer's AdamW (cambrian_trainer.py:242-381).
 """
 from __future__ import annotations
+
+import functools
 
 import torch
 import torch.distributed as dist
@@ -27,11 +31,12 @@ def _round8(n: int) -> int:
 
 class TrainEngine:
     def __init__(self, model: torch.nn.Module, lr: float = 4e-5, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, bucket_mb: float = 256.0, process_group=None):
+                 weight_decay: float = 0.0, bucket_mb: float = 256.0, process_group=None, overlap: bool = True):
         self.model = model
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.overlap = overlap
         self.step_count = 0
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         if not named:
@@ -48,18 +53,18 @@ class TrainEngine:
         self.offsets, self.total = offs, total
         self.flat_p = torch.zeros(total, dtype=torch.bfloat16, device=dev)
         self.flat_g = torch.zeros(total, dtype=torch.bfloat16, device=dev)
-        for p, o in zip(self.params, offs):
+        for i, (p, o) in enumerate(zip(self.params, offs)):
             n = p.numel()
             self.flat_p[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat_p[o:o + n].view(p.shape)          # re-point: compute copy now lives in the flat buffer
             p.main_grad = self.flat_g[o:o + n].view(p.shape)
             p._cb_fresh = set()
-            p._cb_engine = self
+            p._cb_notify = functools.partial(self._on_write, i)
             p.grad = None
         self.master = self.flat_p.float()
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        # buckets: contiguous parameter ranges of ~bucket_mb, reduced in reverse order during backward
+        # buckets: contiguous parameter ranges of ~bucket_mb
         self.buckets = []  # (start_elem, end_elem, [param indices])
         cur, cur_start = [], 0
         limit = int(bucket_mb * 1024 * 1024 / 2)
@@ -75,7 +80,11 @@ class TrainEngine:
         for b, (_, _, idx) in enumerate(self.buckets):
             for i in idx:
                 self._bucket_of[i] = b
-        self._pending = []
+        # contribution accounting for the backward/all-reduce overlap
+        self._expected = None                      # writes per parameter per step, learned on the first step
+        self._writes = [0] * len(self.params)
+        self._remaining = None                     # per bucket: parameters not yet final
+        self._launched = [False] * len(self.buckets)
         self._handles = []
 
     # ---- per-step protocol ---------------------------------------------------------------------------------------
@@ -83,7 +92,29 @@ class TrainEngine:
         for p in self.params:
             p._cb_fresh.clear()
             p.grad = None
+        self._writes = [0] * len(self.params)
+        self._launched = [False] * len(self.buckets)
         self._handles = []
+        if self._expected is not None:
+            self._remaining = [sum(1 for i in idx if self._expected[i] > 0) for (_, _, idx) in self.buckets]
+
+    def _launch_bucket(self, b):
+        s, e, _ = self.buckets[b]
+        self._launched[b] = True
+        self._handles.append(dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def _on_write(self, i):
+        """Called (host side, in stream order) right after a gradient contribution of parameter i was enqueued."""
+        self._writes[i] += 1
+        if self.world == 1 or not self.overlap or self._expected is None:
+            return
+        if self._writes[i] == self._expected[i]:
+            b = self._bucket_of[i]
+            self._remaining[b] -= 1
+            if self._remaining[b] == 0 and not self._launched[b]:
+                # a bucket whose parameters also receive plain-autograd gradients is only final at step()
+                if all(self._expected[j] > 0 for j in self.buckets[b][2]):
+                    self._launch_bucket(b)
 
     def _finalize_unwritten(self):
         """Fold in gradients that reached a parameter through plain autograd (a parameter used by an ordinary torch
@@ -101,11 +132,13 @@ class TrainEngine:
                 p.main_grad.zero_()
 
     def reduce_gradients(self):
-        """Bucketed all-reduce (sum) of the flat gradient buffer; the 1/world average is folded into AdamW."""
+        """All-reduce (sum) every bucket that was not already launched during backward; wait for all of them.
+        The 1/world average is folded into AdamW."""
         if self.world == 1:
             return
-        for (s, e, _) in reversed(self.buckets):
-            self._handles.append(dist.all_reduce(self.flat_g[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        for b in reversed(range(len(self.buckets))):
+            if not self._launched[b]:
+                self._launch_bucket(b)
         for h in self._handles:
             h.wait()
         self._handles = []
@@ -113,6 +146,8 @@ class TrainEngine:
     def step(self):
         self._finalize_unwritten()
         self.reduce_gradients()
+        if self._expected is None:
+            self._expected = list(self._writes)
         self.step_count += 1
         ops.adamw(self.master, self.exp_avg, self.exp_avg_sq, self.flat_g, self.flat_p, self.lr, self.betas[0],
                   self.betas[1], self.eps, self.wd, self.step_count, grad_scale=1.0 / self.world)

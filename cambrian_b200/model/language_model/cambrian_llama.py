@@ -80,12 +80,19 @@ class _FusedGrad:
         mgs = [getattr(p, "main_grad", None) for p in params]
         self.main_grad = None
         self._cb_fresh = None
+        self._params = params
         if all(m is not None for m in mgs) and _adjacent(mgs):
             rows = sum(m.shape[0] for m in mgs)
             K = mgs[0].shape[1]
             self.main_grad = torch.as_strided(mgs[0], (rows, K), (K, 1))
             sets = [getattr(p, "_cb_fresh", None) for p in params]
             self._cb_fresh = _MultiFresh(sets) if all(s is not None for s in sets) else None
+
+    def _cb_notify(self):
+        for p in self._params:
+            n = getattr(p, "_cb_notify", None)
+            if n is not None:
+                n()
 
 
 def rope_tables(config, device):
