@@ -208,7 +208,22 @@ def cpu_reference_sample(threads=None):
     grids (fwd+bwd), ONE Llama-3-8B-shaped decoder layer at S=2048 (fwd+bwd), ONE in-LLM SVA layer (fwd+bwd), and the
     loss head on 128 positions (fwd+bwd).  The per-sample step time is extrapolated by algorithmic FLOPs."""
     from oracle import cambrian_oracle as O
-    torch.set_num_threads(threads or os.cpu_count())
+    # threads = cores this process may actually run on (cgroup / affinity), not os.cpu_count(): oversubscribing a
+    # CPU-limited container makes the fp32 GEMMs an order of magnitude slower
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except AttributeError:
+        usable = os.cpu_count() or 1
+    try:  # cgroup v2 CPU quota
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            usable = max(1, min(usable, int(int(q) / int(per) + 0.5)))
+    except Exception:
+        pass
+    torch.set_num_threads(threads or usable)
+    _w = torch.randn(1024, 1024)
+    for _ in range(3):  # spin up the intra-op thread pool before timing
+        _w = _w @ _w.t() * 1e-3
     g = torch.Generator().manual_seed(0)
     rn = lambda *s, sc=0.02: (torch.randn(*s, generator=g) * sc)
     H, I, nh, nkv, S, V = 4096, 14336, 32, 8, 2048, 128256
@@ -271,13 +286,9 @@ def cpu_reference_sample(threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    vals = []
-    for _ in range(max(1, args.warmup) if args.warmup < 2 else 1):
-        cpu_reference_sample()
-    for _ in range(args.steps):
-        vals.append(cpu_reference_sample())
-    v = statistics.median(x["value"] for x in vals) * world  # each GPU-rank's work would run on the same host cores
-    v = v / world  # one host: the CPU arm processes one sample stream regardless of N
+    # one host CPU regardless of N: the CPU arm processes a single sample stream; each "step" is one bounded sample
+    vals = [cpu_reference_sample() for _ in range(max(1, min(args.steps, 3)))]
+    v = statistics.median(x["value"] for x in vals)
     r = vals[0]
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",

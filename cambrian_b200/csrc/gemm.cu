@@ -38,6 +38,7 @@ struct GemmEpilogue {
   int out_fp32;    // C dtype: 0 bf16, 1 fp32
   int accumulate;  // C += result
   int vec_ok;      // 16-byte vector stores are legal
+  int group_m;     // tile rasterisation: 0 = m fastest over all m-blocks; g > 0 = super-rows of g m-blocks (L2 reuse of A)
 };
 
 template <int BN>
@@ -58,6 +59,25 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case 4: return silu(v);
     default: return v;
   }
+}
+
+
+// tile index -> (m block, n block).  group_m > 0 walks the output in super-rows of group_m m-blocks (all n-blocks of a
+// super-row before the next one) so that a super-row's A panel stays L2-resident while B streams through once per
+// super-row; group_m = 0 keeps one n-block column at a time (B resident, A re-read per column).
+__device__ __forceinline__ void tile_to_mn(int r, int m_blocks, int n_blocks, int group_m, int& mb, int& nb) {
+  if (group_m <= 0) {
+    mb = r % m_blocks;
+    nb = r / m_blocks;
+    return;
+  }
+  const int tpg = group_m * n_blocks;
+  const int g = r / tpg;
+  const int first = g * group_m;
+  const int gs = min(group_m, m_blocks - first);
+  const int w = r - g * tpg;
+  mb = first + w % gs;
+  nb = w / gs;
 }
 
 // Epilogue of one accumulator tile for the 32-column chunks [c_begin, c_end) owned by this warp:
@@ -191,8 +211,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_batch;
         const int r = tile - b * tiles_per_batch;
-        const int m0 = (r % m_blocks) * BM;
-        const int n0 = (r / m_blocks) * BN;
+        int mb_, nb_;
+        tile_to_mn(r, m_blocks, n_blocks, ep.group_m, mb_, nb_);
+        const int m0 = mb_ * BM;
+        const int n0 = nb_ * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -267,8 +289,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
-      const int m0 = (r % m_blocks) * BM;
-      const int n0 = (r / m_blocks) * BN;
+      int mb_, nb_;
+      tile_to_mn(r, m_blocks, n_blocks, ep.group_m, mb_, nb_);
+      const int m0 = mb_ * BM;
+      const int n0 = nb_ * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row = m0 + lane_grp * 32 + lane;
@@ -367,8 +391,10 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int b = tile / tiles_per_batch;
         const int r = tile - b * tiles_per_batch;
-        const int m0 = (r % m_blocks) * (2 * BM) + static_cast<int>(rank) * BM;
-        const int n0 = (r / m_blocks) * BN + static_cast<int>(rank) * Cfg::HALF_N;
+        int mb_, nb_;
+        tile_to_mn(r, m_blocks, n_blocks, ep.group_m, mb_, nb_);
+        const int m0 = mb_ * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = nb_ * BN + static_cast<int>(rank) * Cfg::HALF_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -443,8 +469,10 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
-      const int m0 = (r % m_blocks) * (2 * BM) + static_cast<int>(rank) * BM;
-      const int n0 = (r / m_blocks) * BN;
+      int mb_, nb_;
+      tile_to_mn(r, m_blocks, n_blocks, ep.group_m, mb_, nb_);
+      const int m0 = mb_ * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = nb_ * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row = m0 + lane_grp * 32 + lane;
@@ -626,6 +654,14 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
   if (residual)
     vec = vec && (ldr % 8 == 0) && (bsr % 8 == 0) && ((reinterpret_cast<uintptr_t>(residual) & 15u) == 0);
   ep.vec_ok = vec ? 1 : 0;
+  {
+    static int gm = -1;  // CB_GEMM_GROUP_M: rows of the L2 super-row (default 2048 rows)
+    if (gm < 0) {
+      const char* e = getenv("CB_GEMM_GROUP_M");
+      gm = e ? atoi(e) : 2048;
+    }
+    ep.group_m = gm / (use_2cta ? 2 * BM : BM);
+  }
   if (use_2cta) return dispatch_2cta(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
   switch (bn) {
     case 256: return dispatch_major<256>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);

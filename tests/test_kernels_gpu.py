@@ -34,7 +34,7 @@ def test_gemm_epilogues(capsys):
 
 
 def test_gemm_cta_pair_kernel(capsys):
-    _run("probe1", "gemm_2cta", capsys, 30)
+    _run("probe1", "gemm_2cta", capsys, 24)
 
 
 def test_sva_window_attention_fwd_bwd(capsys):
