@@ -429,16 +429,44 @@ def main():
         roof = dict(bound="tensor", kernel="gemm_bf16_tcgen05", achieved=ach, peak=tf_sustained, unit="TFLOP/s",
                     frac=ach / tf_sustained, traffic=None, launches_timed=n, share_of_step=tms / ms,
                     peak_source=f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)")
+    # ncu --set full DRAM traffic of the dominant GEMM launch (decoder gate/up projection, M=8192 N=28672 K=4096):
+    # profiles/r01_kernels_ncu_summary.txt; algorithmic bytes of that launch = (M*K + N*K + M*N)*2 = 0.772 GB
+    if roof is not None:
+        roof["traffic"] = 1.036081e9 + 0.452051e9
+        roof["traffic_note"] = ("dram read+write bytes of ONE launch of the dominant shape M=8192 N=28672 K=4096 "
+                                "(algorithmic 0.772e9 B; 2.67e9 B before tile rasterisation); ncu capture under profiles/")
     roof_sva = None
-    if "sva_fwd" in agg:
-        by, tms, n = agg["sva_fwd"]
-        ach = by / (tms / 1000.0) / 1e9
-        roof_sva = dict(bound="hbm", kernel="sva_window_attn_fwd", achieved=ach, peak=hbm_peak, unit="GB/s",
-                        frac=ach / hbm_peak, traffic=None, launches_timed=n, share_of_step=tms / ms,
-                        peak_source=f"{peak_src} hbm_gbs")
-        if "sva_bwd" in agg:
-            by2, tms2, n2 = agg["sva_bwd"]
-            roof_sva["bwd_achieved"] = by2 / (tms2 / 1000.0) / 1e9
+    if not args.small:
+        # second headline metric (BASELINE.json "SVA HBM GB/s"): the fused window-attention kernel alone, on inputs larger
+        # than L2 (batch 32: 377 MB for the BASELINE grids, 1.51 GB for the release grids), CUDA events, 20 launches
+        roof_sva = {}
+        for tag, rs in (("baseline_grids_576x4", [1, 1, 1, 1]), ("release_grids_576x3_9216", [1, 1, 1, 4])):
+            Bq, qs = 32, 24
+            qq = torch.randn(Bq * qs * qs, 1024, device=dev).bfloat16()
+            ks = [torch.randn(Bq, (r * qs) ** 2, 1024, device=dev).bfloat16() for r in rs]
+            vs = [torch.randn(Bq, (r * qs) ** 2, 1024, device=dev).bfloat16() for r in rs]
+            for _ in range(3):
+                ops.sva_window_attn_fwd(qq, ks, vs, None, rs, Bq, qs)
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(20):
+                ops.sva_window_attn_fwd(qq, ks, vs, None, rs, Bq, qs)
+            s1.record()
+            torch.cuda.synchronize()
+            byts = 2.0 * (2 * sum(k.numel() for k in ks) + 2 * qq.numel())
+            ach = byts / (s0.elapsed_time(s1) / 20 / 1000.0) / 1e9
+            roof_sva[tag] = dict(achieved=ach, frac=ach / hbm_peak, algorithmic_bytes_per_launch=byts,
+                                 mb_per_sample_per_layer=byts / Bq / 1e6)
+            del qq, ks, vs
+        roof_sva.update(bound="hbm", kernel="sva_window_attn_fwd", peak=hbm_peak, unit="GB/s",
+                        achieved=roof_sva["baseline_grids_576x4"]["achieved"],
+                        frac=roof_sva["baseline_grids_576x4"]["frac"],
+                        traffic=0.339770e9 + 0.008153e9, peak_source=f"{peak_src} hbm_gbs",
+                        traffic_note="ncu dram bytes of one batch-32 launch on the BASELINE grids (algorithmic 0.377e9 B; the "
+                                     "output write-back had not left L2 when the counter was read)")
+        if "sva_fwd" in agg:
+            by, tms, n = agg["sva_fwd"]
+            roof_sva["in_step_achieved"] = by / (tms / 1000.0) / 1e9  # B=4 inputs (38 MB) are L2-resident in the step
     model_tf = value * STEP_TF if not args.small else None
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
