@@ -576,27 +576,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
       {
+        // pull the whole dQ row out of TMEM first and release region B immediately: the next iteration's S^T / dP^T MMAs
+        // then overlap with the (slow) global reductions below
         const int qi = qi0 + row;
         float* dqp = p.dq_acc + (((long long)b * p.Sq + qi) * p.nh + h) * p.hd;
-#pragma unroll 1
-        for (int c = 0; c < Cfg::OCH; ++c) {
-          uint32_t r[32];
-          tmem_ld32(tB + lane_off + c * 32, r);
-          tmem_ld_wait();
-          if (qi < p.Sq) {
+        uint32_t r[Cfg::OCH * 32];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int d0 = c * 32 + u * 4;
-              if (d0 < p.hd)
-                atomicAdd(reinterpret_cast<float4*>(dqp + d0),
-                          make_float4(__uint_as_float(r[u * 4]), __uint_as_float(r[u * 4 + 1]),
-                                      __uint_as_float(r[u * 4 + 2]), __uint_as_float(r[u * 4 + 3])));
-            }
+        for (int c = 0; c < Cfg::OCH; ++c) tmem_ld32(tB + lane_off + c * 32, r + c * 32);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dq_done);
+        if (qi < p.Sq) {
+#pragma unroll
+          for (int u = 0; u < Cfg::OCH * 8; ++u) {
+            const int d0 = u * 4;
+            if (d0 < p.hd)
+              atomicAdd(reinterpret_cast<float4*>(dqp + d0),
+                        make_float4(__uint_as_float(r[u * 4]), __uint_as_float(r[u * 4 + 1]),
+                                    __uint_as_float(r[u * 4 + 2]), __uint_as_float(r[u * 4 + 3])));
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(dq_done);
     }
     // ---- epilogue: dK (x softmax scale), dV -> bf16
     if (n_iter > 0) {

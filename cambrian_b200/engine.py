@@ -31,12 +31,21 @@ def _round8(n: int) -> int:
 
 class TrainEngine:
     def __init__(self, model: torch.nn.Module, lr: float = 4e-5, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, bucket_mb: float = 256.0, process_group=None, overlap: bool = True):
+                 weight_decay: float = 0.0, bucket_mb: float = 256.0, process_group=None, overlap: bool = True,
+                 zero_stage: int = 0):
+        """zero_stage = 0: replicated optimizer state (DDP, BASELINE config 3).
+        zero_stage = 2: optimizer state (fp32 master + Adam moments, 12 of the 16 bytes/param) sharded across ranks
+        (BASELINE config 4, scripts/zero2.json): gradients are reduce-scattered, each rank updates its 1/world slice of
+        the flat buffer, the updated bf16 parameters are all-gathered."""
         self.model = model
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
-        self.overlap = overlap
+        self.overlap = overlap and zero_stage == 0
+        self.zero_stage = zero_stage
+        if zero_stage not in (0, 2):
+            raise ValueError("zero_stage must be 0 or 2")
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         self.step_count = 0
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         if not named:
@@ -50,7 +59,12 @@ class TrainEngine:
                 raise ValueError("TrainEngine expects bf16 parameters (fp32 masters are kept by the engine)")
             offs.append(total)
             total += _round8(p.numel())
-        self.offsets, self.total = offs, total
+        self.offsets = offs
+        self.shard = 0
+        if zero_stage == 2:
+            self.shard = _round8((total + self.world - 1) // self.world)
+            total = self.shard * self.world          # pad so every rank owns an equal, 16-byte aligned slice
+        self.total = total
         self.flat_p = torch.zeros(total, dtype=torch.bfloat16, device=dev)
         self.flat_g = torch.zeros(total, dtype=torch.bfloat16, device=dev)
         for i, (p, o) in enumerate(zip(self.params, offs)):
@@ -61,9 +75,16 @@ class TrainEngine:
             p._cb_fresh = set()
             p._cb_notify = functools.partial(self._on_write, i)
             p.grad = None
-        self.master = self.flat_p.float()
-        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        if zero_stage == 2:
+            lo = self.rank * self.shard
+            self.master = self.flat_p[lo:lo + self.shard].float()
+            self.exp_avg = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+            self.exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+            self.shard_g = torch.zeros(self.shard, dtype=torch.bfloat16, device=dev)
+        else:
+            self.master = self.flat_p.float()
+            self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         # buckets: contiguous parameter ranges of ~bucket_mb
         self.buckets = []  # (start_elem, end_elem, [param indices])
         cur, cur_start = [], 0
@@ -143,14 +164,36 @@ class TrainEngine:
             h.wait()
         self._handles = []
 
+    def _zero2_step(self):
+        lo = self.rank * self.shard
+        if self.world > 1:
+            if dist.get_backend(self.pg) == "nccl":
+                dist.reduce_scatter_tensor(self.shard_g, self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+                g = self.shard_g
+            else:  # gloo (CPU tests) has no reduce_scatter_tensor: all-reduce, then keep the local slice
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.pg)
+                g = self.flat_g[lo:lo + self.shard]
+        else:
+            g = self.flat_g
+        p16 = self.flat_p[lo:lo + self.shard]
+        self._adamw(self.master, self.exp_avg, self.exp_avg_sq, g, p16)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.flat_p, p16.clone(), group=self.pg)
+
+    def _adamw(self, master, m, v, g, p16):
+        ops.adamw(master, m, v, g, p16, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count,
+                  grad_scale=1.0 / self.world)
+
     def step(self):
         self._finalize_unwritten()
-        self.reduce_gradients()
         if self._expected is None:
             self._expected = list(self._writes)
         self.step_count += 1
-        ops.adamw(self.master, self.exp_avg, self.exp_avg_sq, self.flat_g, self.flat_p, self.lr, self.betas[0],
-                  self.betas[1], self.eps, self.wd, self.step_count, grad_scale=1.0 / self.world)
+        if self.zero_stage == 2:
+            self._zero2_step()
+            return
+        self.reduce_gradients()
+        self._adamw(self.master, self.exp_avg, self.exp_avg_sq, self.flat_g, self.flat_p)
 
     # ---- convenience ---------------------------------------------------------------------------------------------
     def train_step(self, **batch):
@@ -161,4 +204,5 @@ class TrainEngine:
         return out.loss
 
     def state_bytes(self):
-        return self.total * (2 + 2 + 4 + 4 + 4)
+        opt = (self.shard if self.zero_stage == 2 else self.total) * 12
+        return self.total * 4 + opt

@@ -170,6 +170,50 @@ def _dp_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _zero2_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cambrian_b200 import engine as E
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(16, 24, bias=True), torch.nn.Linear(24, 9, bias=False)).bfloat16()
+    eng = E.TrainEngine(model, zero_stage=2)
+    assert eng.total == eng.shard * world and eng.master.numel() == eng.shard   # optimizer state is sharded
+    # stand-in for the CUDA AdamW kernel (not available on CPU): plain SGD on the fp32 master slice
+    def sgd(master, m, v, g, p16):
+        master.sub_(0.5 * g.float() / world)
+        p16.copy_(master.to(torch.bfloat16))
+    eng._adamw = sgd
+    before = eng.flat_p.float().clone()
+    eng.zero_grad()
+    for i, p in enumerate(eng.params):
+        p.main_grad.fill_(float(rank + 1) * 0.25 * (i + 1))
+        p._cb_fresh.add("all")
+    eng.step()
+    # expected: every element moved by 0.5 * mean over ranks of its gradient = 0.5 * 0.375 * (i+1)
+    ok = True
+    for i, (p, o) in enumerate(zip(eng.params, eng.offsets)):
+        exp = before[o:o + p.numel()] - 0.5 * 0.375 * (i + 1)
+        ok &= torch.allclose(eng.flat_p[o:o + p.numel()].float(), exp.to(torch.bfloat16).float(), atol=2e-2)
+        ok &= p.data_ptr() == eng.flat_p.data_ptr() + 2 * o     # parameters still alias the (all-gathered) flat buffer
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_zero2_sharded_optimizer_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_zero2_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
+
+
 def test_gradient_allreduce_two_ranks_gloo():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
