@@ -364,7 +364,7 @@ struct BwdCfg {
 };
 
 template <int HDP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, AttnBwdParams p) {
   using Cfg = BwdCfg<HDP>;
@@ -413,9 +413,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(qd_empty(s), 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, 256);
     mbar_init(dq_full, 1);
-    mbar_init(dq_done, 128);
+    mbar_init(dq_done, 256);
     mbar_fence_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 512);
@@ -503,9 +503,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    const int row = warp * 32 + lane;  // key row of this CTA's tile (phase 1) / query row of the tile (phase 2)
+    // 8 compute warps (0-3 and 6-9): two warps per TMEM lane quarter, each owning half of the columns of every
+    // row — the per-element work has no row reductions, so the split needs no exchange and halves the serial thread phase
+    const int row = (warp & 3) * 32 + lane;  // key row of this CTA's tile (phase 1) / query row of the tile (phase 2)
+    const int ch = warp >= 6 ? 1 : 0;        // column half
     const int kidx = k0 + row;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const bool key_ok = kidx < p.Skv && (!p.kmask || p.kmask[(size_t)b * p.Skv + kidx]);
     for (int it = 0; it < n_iter; ++it) {
       const int h = g * G + it / n_i;
@@ -517,7 +520,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         stat[row] = qi < p.Sq ? p.lse[so] : INFINITY;
         stat[128 + row] = qi < p.Sq ? p.delta[so] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(sdp_full, it & 1);
       tc_fence_after();
       // queries visible to this key: qi + coff >= kidx, qi < Sq
@@ -525,7 +528,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (p.causal) qmin = kidx - coff - qi0;
       const int qmax = p.Sq - qi0;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
         uint32_t rs[32], rd[32];
         tmem_ld32(tA + lane_off + c * 32, rs);
         tmem_ld32(tB + lane_off + c * 32, rd);
@@ -580,16 +583,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // then overlap with the (slow) global reductions below
         const int qi = qi0 + row;
         float* dqp = p.dq_acc + (((long long)b * p.Sq + qi) * p.nh + h) * p.hd;
-        uint32_t r[Cfg::OCH * 32];
+        constexpr int HC = Cfg::OCH / 2;  // 32-column chunks of the dQ row owned by this warp
+        uint32_t r[HC * 32];
 #pragma unroll
-        for (int c = 0; c < Cfg::OCH; ++c) tmem_ld32(tB + lane_off + c * 32, r + c * 32);
+        for (int c = 0; c < HC; ++c) tmem_ld32(tB + lane_off + (ch * HC + c) * 32, r + c * 32);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(dq_done);
         if (qi < p.Sq) {
 #pragma unroll
-          for (int u = 0; u < Cfg::OCH * 8; ++u) {
-            const int d0 = u * 4;
+          for (int u = 0; u < HC * 8; ++u) {
+            const int d0 = ch * HC * 32 + u * 4;
             if (d0 < p.hd)
               atomicAdd(reinterpret_cast<float4*>(dqp + d0),
                         make_float4(__uint_as_float(r[u * 4]), __uint_as_float(r[u * 4 + 1]),
@@ -604,7 +608,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       bf16* dkp = p.dk + (long long)b * p.dk_bs + (long long)kidx * p.dk_ss + (long long)g * p.hd;
       bf16* dvp = p.dv + (long long)b * p.dv_bs + (long long)kidx * p.dv_ss + (long long)g * p.hd;
 #pragma unroll 1
-      for (int c = 0; c < Cfg::OCH; ++c) {
+      for (int c = ch * (Cfg::OCH / 2); c < (ch + 1) * (Cfg::OCH / 2); ++c) {
         uint32_t r1[32], r2[32];
         tmem_ld32(tdK + lane_off + c * 32, r1);
         tmem_ld32(tdV + lane_off + c * 32, r2);
@@ -630,7 +634,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       bf16* dkp = p.dk + (long long)b * p.dk_bs + (long long)kidx * p.dk_ss + (long long)g * p.hd;
       bf16* dvp = p.dv + (long long)b * p.dv_bs + (long long)kidx * p.dv_ss + (long long)g * p.hd;
       const uint4 z = make_uint4(0, 0, 0, 0);
-      for (int d0 = 0; d0 < p.hd; d0 += 8) {
+      for (int d0 = ch * (p.hd / 2); d0 < (ch + 1) * (p.hd / 2); d0 += 8) {
         *reinterpret_cast<uint4*>(dkp + d0) = z;
         *reinterpret_cast<uint4*>(dvp + d0) = z;
       }
@@ -737,7 +741,7 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     attr = true;
   }
   dim3 grid((p.Skv + 127) / 128, p.nkv, p.B);
-  kern<<<grid, 192, Cfg::SMEM, st>>>(tq, tk, tv, tdo, p);
+  kern<<<grid, 320, Cfg::SMEM, st>>>(tq, tk, tv, tdo, p);
   CB_CUDA_LAUNCH_CHECK("attn_bwd");
   return CB_OK;
 }
