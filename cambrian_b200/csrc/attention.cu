@@ -527,10 +527,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       int qmin = 0;
       if (p.causal) qmin = kidx - coff - qi0;
       const int qmax = p.Sq - qi0;
-#pragma unroll 1
-      for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
-        uint32_t rs[32], rd[32];
-        tmem_ld32(tA + lane_off + c * 32, rs);
+      // P^T is written in place over S^T (columns [0, 64) of region A), i.e. over columns the OTHER half's warp still has
+      // to read: pull both S^T chunks of this warp into registers and meet at a barrier before anyone stores P^T
+      uint32_t rs2[64];
+      tmem_ld32(tA + lane_off + (2 * ch) * 32, rs2);
+      tmem_ld32(tA + lane_off + (2 * ch + 1) * 32, rs2 + 32);
+      tmem_ld_wait();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * ch + cc;
+        const uint32_t* rs = rs2 + cc * 32;
+        uint32_t rd[32];
         tmem_ld32(tB + lane_off + c * 32, rd);
         tmem_ld_wait();
         // branch-free visibility mask for the 32 queries of this chunk

@@ -79,8 +79,15 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
   return 0.5f * x * (1.0f + tanhf(u));
 }
-__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// tanh-GELU with tanh(u) = 1 - 2 / (1 + e^{2u}) on MUFU.EX2 / MUFU.RCP (tanhf's software path is branchy)
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
+  return 0.5f * x * (1.0f + t);
+}
+// __fdividef: MUFU.RCP + FMUL (2 ulp) instead of the IEEE division's Newton iterations + slow-path branch
+__device__ __forceinline__ float quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // single MUFU.EX2 (2^-inf = +0, no denormal range fix-up branches): softmax inner loops
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;

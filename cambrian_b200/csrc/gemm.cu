@@ -51,14 +51,15 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case 1: return gelu_erf(v);
-    case 2: return gelu_tanh(v);
-    case 3: return quick_gelu(v);
-    case 4: return silu(v);
-    default: return v;
-  }
+// activation selected at COMPILE time: a per-element runtime switch (plus slow-path erff / tanhf) made the epilogue of
+// short-K GEMMs 3.4x slower than their mainloop (profiles/r01_gemm_epilogue_microbench.log)
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+  if constexpr (ACT == 1) return gelu_erf(v);
+  else if constexpr (ACT == 2) return gelu_tanh_fast(v);
+  else if constexpr (ACT == 3) return quick_gelu(v);
+  else if constexpr (ACT == 4) return silu(v);
+  else return v;
 }
 
 
@@ -82,18 +83,36 @@ __device__ __forceinline__ void tile_to_mn(int r, int m_blocks, int n_blocks, in
 
 // Epilogue of one accumulator tile for the 32-column chunks [c_begin, c_end) owned by this warp:
 // tcgen05.ld -> alpha, bias, activation, LayerScale, residual, accumulate -> bf16 / fp32 stores.
-template <int BN>
+template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_t taddr, int row, bool row_ok, int b,
-                                                 int n0, int N, int c_begin, int c_end) {
+                                                 int n0, int N, int c_begin) {
+  // One warp drains NCH 32-column chunks of its 32 accumulator rows.  The loop is fully unrolled and software-pipelined:
+  // the tcgen05.ld of chunk i+1 and the bias / column-scale / residual vectors of chunk i are in flight while chunk i-1's
+  // arithmetic retires — with only two epilogue warps per scheduler nothing else hides those latencies.
+  constexpr int NCH = BN / 64;
   const long long c_off = static_cast<long long>(b) * ep.bsc + static_cast<long long>(row) * ep.ldc;
   const long long r_off = static_cast<long long>(b) * ep.bsr + static_cast<long long>(row) * ep.ldr;
-#pragma unroll 1
-  for (int c = c_begin; c < c_end; ++c) {
+  const bool vec = ep.vec_ok;
+  const bool pre_bias = ep.bias && vec, pre_scale = ep.colscale && vec, pre_res = ep.residual && vec && row_ok;
+  uint32_t rr[2][32];
+  if (n0 + c_begin * 32 < N) tmem_ld32(taddr + c_begin * 32, rr[0]);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = c_begin + i;
     const int col0 = n0 + c * 32;
     if (col0 >= N) break;  // warp-uniform
-    uint32_t rr[32];
-    tmem_ld32(taddr + c * 32, rr);
+    uint4 qb[4], qs[4], qr[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = col0 + g * 8;
+      if (col < N) {
+        if (pre_bias) qb[g] = *reinterpret_cast<const uint4*>(ep.bias + col);
+        if (pre_scale) qs[g] = *reinterpret_cast<const uint4*>(ep.colscale + col);
+        if (pre_res) qr[g] = ldg_nc(ep.residual + r_off + col);
+      }
+    }
     tmem_ld_wait();
+    if (i + 1 < NCH && col0 + 32 < N) tmem_ld32(taddr + (c + 1) * 32, rr[(i + 1) & 1]);
     if (row_ok) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -101,22 +120,36 @@ __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_
         if (col >= N) break;
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[g * 8 + j]) * ep.alpha;
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[i & 1][g * 8 + j]) * ep.alpha;
         const int nvalid = min(8, N - col);
         if (ep.bias) {
-          for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(ep.bias[col + j]);
-        }
-        if (ep.act) {
+          if (vec) {  // N % 8 == 0 and 16-byte aligned vectors (host-checked): one load instead of eight
+            float t[8];
+            unpack8(qb[g], t);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], ep.act);
+            for (int j = 0; j < 8; ++j) v[j] += t[j];
+          } else {
+            for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(ep.bias[col + j]);
+          }
+        }
+        if (ACT != 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = apply_act<ACT>(v[j]);
         }
         if (ep.colscale) {
-          for (int j = 0; j < nvalid; ++j) v[j] *= __bfloat162float(ep.colscale[col + j]);
+          if (vec) {
+            float t[8];
+            unpack8(qs[g], t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= t[j];
+          } else {
+            for (int j = 0; j < nvalid; ++j) v[j] *= __bfloat162float(ep.colscale[col + j]);
+          }
         }
         if (ep.residual) {
-          if (ep.vec_ok) {
+          if (vec) {
             float t[8];
-            unpack8(*reinterpret_cast<const uint4*>(ep.residual + r_off + col), t);
+            unpack8(qr[g], t);
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] += t[j];
           } else {
@@ -125,7 +158,7 @@ __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_
         }
         if (ep.out_fp32) {
           float* cp = reinterpret_cast<float*>(ep.C) + c_off + col;
-          if (ep.vec_ok) {
+          if (vec) {
             float4* c4 = reinterpret_cast<float4*>(cp);
             if (ep.accumulate) {
               const float4 o0 = c4[0], o1 = c4[1];
@@ -139,7 +172,7 @@ __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_
           }
         } else {
           bf16* cp = reinterpret_cast<bf16*>(ep.C) + c_off + col;
-          if (ep.vec_ok) {
+          if (vec) {
             if (ep.accumulate) {
               float t[8];
               unpack8(*reinterpret_cast<const uint4*>(cp), t);
@@ -157,7 +190,7 @@ __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int ACT>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   int M, int N, int K, int batch, GemmEpilogue ep) {
@@ -299,7 +332,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
-      epilogue_columns<BN>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64), (col_half + 1) * (BN / 64));
+      epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -335,7 +368,7 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                        int K, int batch, GemmEpilogue ep) {
@@ -479,7 +512,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
-      epilogue_columns<BN>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64), (col_half + 1) * (BN / 64));
+      epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // leader's barrier
@@ -542,11 +575,11 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return CB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int ACT>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int batch,
                        const GemmEpilogue& ep, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN, ACT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -560,11 +593,11 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   return CB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int ACT>
 static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int batch,
                         const GemmEpilogue& ep, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
-  auto kern = gemm_bf16_tcgen05_2cta<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_tcgen05_2cta<BN, A_MN, B_MN, ACT>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -581,10 +614,18 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
 
 static int dispatch_2cta(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
                          int batch, const GemmEpilogue& ep, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_gemm2<256, false, false>(tmA, tmB, M, N, K, batch, ep, stream);
-  if (!a_mn && b_mn) return launch_gemm2<256, false, true>(tmA, tmB, M, N, K, batch, ep, stream);
-  if (a_mn && !b_mn) return launch_gemm2<256, true, false>(tmA, tmB, M, N, K, batch, ep, stream);
-  return launch_gemm2<256, true, true>(tmA, tmB, M, N, K, batch, ep, stream);
+  if (!a_mn && !b_mn) {  // forward layout: the only one that carries a fused activation
+    switch (ep.act) {
+      case 1: return launch_gemm2<256, false, false, 1>(tmA, tmB, M, N, K, batch, ep, stream);
+      case 2: return launch_gemm2<256, false, false, 2>(tmA, tmB, M, N, K, batch, ep, stream);
+      case 3: return launch_gemm2<256, false, false, 3>(tmA, tmB, M, N, K, batch, ep, stream);
+      case 4: return launch_gemm2<256, false, false, 4>(tmA, tmB, M, N, K, batch, ep, stream);
+      default: return launch_gemm2<256, false, false, 0>(tmA, tmB, M, N, K, batch, ep, stream);
+    }
+  }
+  if (!a_mn && b_mn) return launch_gemm2<256, false, true, 0>(tmA, tmB, M, N, K, batch, ep, stream);
+  if (a_mn && !b_mn) return launch_gemm2<256, true, false, 0>(tmA, tmB, M, N, K, batch, ep, stream);
+  return launch_gemm2<256, true, true, 0>(tmA, tmB, M, N, K, batch, ep, stream);
 }
 
 // CB_GEMM_2CTA=0 disables the CTA-pair kernel (read once)
@@ -600,10 +641,18 @@ static bool two_cta_enabled() {
 template <int BN>
 static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N,
                           int K, int batch, const GemmEpilogue& ep, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(tmA, tmB, M, N, K, batch, ep, stream);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(tmA, tmB, M, N, K, batch, ep, stream);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(tmA, tmB, M, N, K, batch, ep, stream);
-  return launch_gemm<BN, true, true>(tmA, tmB, M, N, K, batch, ep, stream);
+  if (!a_mn && !b_mn) {
+    switch (ep.act) {
+      case 1: return launch_gemm<BN, false, false, 1>(tmA, tmB, M, N, K, batch, ep, stream);
+      case 2: return launch_gemm<BN, false, false, 2>(tmA, tmB, M, N, K, batch, ep, stream);
+      case 3: return launch_gemm<BN, false, false, 3>(tmA, tmB, M, N, K, batch, ep, stream);
+      case 4: return launch_gemm<BN, false, false, 4>(tmA, tmB, M, N, K, batch, ep, stream);
+      default: return launch_gemm<BN, false, false, 0>(tmA, tmB, M, N, K, batch, ep, stream);
+    }
+  }
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, 0>(tmA, tmB, M, N, K, batch, ep, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, 0>(tmA, tmB, M, N, K, batch, ep, stream);
+  return launch_gemm<BN, true, true, 0>(tmA, tmB, M, N, K, batch, ep, stream);
 }
 
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int batch, long long lda,
@@ -614,6 +663,7 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
                batch);
   CB_CHECK_ARG(A && B && C, "gemm: null operand");
   CB_CHECK_ARG(act >= 0 && act <= 4, "gemm: unknown activation %d", act);
+  CB_CHECK_ARG(act == 0 || (!a_mn && !b_mn), "gemm: a fused activation needs K-major operands (forward layout)");
   CUtensorMap tmA, tmB;
   int rc;
   int bn = force_bn;
@@ -653,6 +703,8 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
              ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
   if (residual)
     vec = vec && (ldr % 8 == 0) && (bsr % 8 == 0) && ((reinterpret_cast<uintptr_t>(residual) & 15u) == 0);
+  if (bias) vec = vec && ((reinterpret_cast<uintptr_t>(bias) & 15u) == 0);
+  if (colscale) vec = vec && ((reinterpret_cast<uintptr_t>(colscale) & 15u) == 0);
   ep.vec_ok = vec ? 1 : 0;
   {
     static int gm = -1;  // CB_GEMM_GROUP_M: rows of the L2 super-row (default 2048 rows)
