@@ -35,7 +35,7 @@ def _compile(src: Path, verbose: bool) -> Path:
     obj = OBJ / (src.stem + ".o")
     deps = list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "cambrian_b200.h"]
     if _newer(src, obj, deps):
-        cmd = [NVCC, *FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [NVCC, *FLAGS, *os.environ.get("CB_NVCC_EXTRA", "").split(), "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")

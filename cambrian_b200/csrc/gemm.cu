@@ -83,110 +83,128 @@ __device__ __forceinline__ void tile_to_mn(int r, int m_blocks, int n_blocks, in
 
 // Epilogue of one accumulator tile for the 32-column chunks [c_begin, c_end) owned by this warp:
 // tcgen05.ld -> alpha, bias, activation, LayerScale, residual, accumulate -> bf16 / fp32 stores.
+#ifndef CB_EPI_INNER
+#define CB_EPI_INNER 1  // measured: 1 beats 2 and 4 (profiles/r01_gemm_epilogue_microbench.log) — code size matters more than ILP
+#endif
+
+// Rare path (N % 8 != 0 or a misaligned vector operand): element-at-a-time through a local array, deliberately NOT
+// unrolled — the unrolled scalar fallbacks used to triple the kernel's code size (210 KB of SASS, instruction-cache
+// misses on the hot path, profiles/r01_gemm_epilogue_microbench.log).
+template <int ACT>
+__device__ __noinline__ void epilogue_chunk_scalar(const GemmEpilogue& ep, const uint32_t* rr, long long c_off,
+                                                   long long r_off, int col0, int N) {
+  const int n = min(32, N - col0);
+#pragma unroll 1
+  for (int j = 0; j < n; ++j) {
+    const int col = col0 + j;
+    float v = __uint_as_float(rr[j]) * ep.alpha;
+    if (ep.bias) v += __bfloat162float(ep.bias[col]);
+    v = apply_act<ACT>(v);
+    if (ep.colscale) v *= __bfloat162float(ep.colscale[col]);
+    if (ep.residual) v += __bfloat162float(ep.residual[r_off + col]);
+    if (ep.out_fp32) {
+      float* cp = reinterpret_cast<float*>(ep.C) + c_off + col;
+      *cp = ep.accumulate ? *cp + v : v;
+    } else {
+      bf16* cp = reinterpret_cast<bf16*>(ep.C) + c_off + col;
+      *cp = __float2bfloat16(ep.accumulate ? __bfloat162float(*cp) + v : v);
+    }
+  }
+}
+
 template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_t taddr, int row, bool row_ok, int b,
                                                  int n0, int N, int c_begin) {
-  // One warp drains NCH 32-column chunks of its 32 accumulator rows.  The loop is fully unrolled and software-pipelined:
-  // the tcgen05.ld of chunk i+1 and the bias / column-scale / residual vectors of chunk i are in flight while chunk i-1's
-  // arithmetic retires — with only two epilogue warps per scheduler nothing else hides those latencies.
+  // One warp drains NCH 32-column chunks of its 32 accumulator rows, software-pipelined: the tcgen05.ld of chunk i+1 and
+  // the bias / column-scale / residual vectors of chunk i are in flight while chunk i's arithmetic runs — with only two
+  // epilogue warps per scheduler nothing else hides those latencies.
   constexpr int NCH = BN / 64;
   const long long c_off = static_cast<long long>(b) * ep.bsc + static_cast<long long>(row) * ep.ldc;
   const long long r_off = static_cast<long long>(b) * ep.bsr + static_cast<long long>(row) * ep.ldr;
-  const bool vec = ep.vec_ok;
-  const bool pre_bias = ep.bias && vec, pre_scale = ep.colscale && vec, pre_res = ep.residual && vec && row_ok;
+  const bool vec = ep.vec_ok;  // N % 8 == 0 and 16-byte aligned vectors (host-checked)
+  const bool has_bias = ep.bias != nullptr, has_scale = ep.colscale != nullptr;
+  const bool has_res = ep.residual != nullptr;
+  // chunks are unrolled (and pipelined) in groups of INNER; the group loop itself is not unrolled to bound code size
+  constexpr int INNER = NCH < CB_EPI_INNER ? NCH : CB_EPI_INNER;
   uint32_t rr[2][32];
-  if (n0 + c_begin * 32 < N) tmem_ld32(taddr + c_begin * 32, rr[0]);
+#pragma unroll 1
+  for (int o = 0; o < NCH; o += INNER) {
+  if (n0 + (c_begin + o) * 32 >= N) break;  // warp-uniform
+  tmem_ld32(taddr + (c_begin + o) * 32, rr[0]);
 #pragma unroll
-  for (int i = 0; i < NCH; ++i) {
-    const int c = c_begin + i;
+  for (int i = 0; i < INNER; ++i) {
+    const int c = c_begin + o + i;
     const int col0 = n0 + c * 32;
     if (col0 >= N) break;  // warp-uniform
     uint4 qb[4], qs[4], qr[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int col = col0 + g * 8;
-      if (col < N) {
-        if (pre_bias) qb[g] = *reinterpret_cast<const uint4*>(ep.bias + col);
-        if (pre_scale) qs[g] = *reinterpret_cast<const uint4*>(ep.colscale + col);
-        if (pre_res) qr[g] = ldg_nc(ep.residual + r_off + col);
-      }
-    }
-    tmem_ld_wait();
-    if (i + 1 < NCH && col0 + 32 < N) tmem_ld32(taddr + (c + 1) * 32, rr[(i + 1) & 1]);
-    if (row_ok) {
+    if (vec) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int col = col0 + g * 8;
-        if (col >= N) break;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[i & 1][g * 8 + j]) * ep.alpha;
-        const int nvalid = min(8, N - col);
-        if (ep.bias) {
-          if (vec) {  // N % 8 == 0 and 16-byte aligned vectors (host-checked): one load instead of eight
-            float t[8];
-            unpack8(qb[g], t);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += t[j];
-          } else {
-            for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(ep.bias[col + j]);
-          }
-        }
-        if (ACT != 0) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = apply_act<ACT>(v[j]);
-        }
-        if (ep.colscale) {
-          if (vec) {
-            float t[8];
-            unpack8(qs[g], t);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= t[j];
-          } else {
-            for (int j = 0; j < nvalid; ++j) v[j] *= __bfloat162float(ep.colscale[col + j]);
-          }
-        }
-        if (ep.residual) {
-          if (vec) {
-            float t[8];
-            unpack8(qr[g], t);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += t[j];
-          } else {
-            for (int j = 0; j < nvalid; ++j) v[j] += __bfloat162float(ep.residual[r_off + col + j]);
-          }
-        }
-        if (ep.out_fp32) {
-          float* cp = reinterpret_cast<float*>(ep.C) + c_off + col;
-          if (vec) {
-            float4* c4 = reinterpret_cast<float4*>(cp);
-            if (ep.accumulate) {
-              const float4 o0 = c4[0], o1 = c4[1];
-              v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
-              v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
-            }
-            c4[0] = make_float4(v[0], v[1], v[2], v[3]);
-            c4[1] = make_float4(v[4], v[5], v[6], v[7]);
-          } else {
-            for (int j = 0; j < nvalid; ++j) cp[j] = ep.accumulate ? cp[j] + v[j] : v[j];
-          }
-        } else {
-          bf16* cp = reinterpret_cast<bf16*>(ep.C) + c_off + col;
-          if (vec) {
-            if (ep.accumulate) {
-              float t[8];
-              unpack8(*reinterpret_cast<const uint4*>(cp), t);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += t[j];
-            }
-            *reinterpret_cast<uint4*>(cp) = pack8(v);
-          } else {
-            for (int j = 0; j < nvalid; ++j)
-              cp[j] = __float2bfloat16(ep.accumulate ? __bfloat162float(cp[j]) + v[j] : v[j]);
-          }
+        if (col < N) {
+          if (has_bias) qb[g] = *reinterpret_cast<const uint4*>(ep.bias + col);
+          if (has_scale) qs[g] = *reinterpret_cast<const uint4*>(ep.colscale + col);
+          if (has_res && row_ok) qr[g] = ldg_nc(ep.residual + r_off + col);
         }
       }
     }
+    tmem_ld_wait();
+    if (i + 1 < INNER && col0 + 32 < N) tmem_ld32(taddr + (c + 1) * 32, rr[(i + 1) & 1]);
+    if (!row_ok) continue;
+    if (!vec) {
+      epilogue_chunk_scalar<ACT>(ep, rr[i & 1], c_off, r_off, col0, N);
+      continue;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = col0 + g * 8;
+      if (col >= N) break;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[i & 1][g * 8 + j]) * ep.alpha;
+      if (has_bias) {
+        float t[8];
+        unpack8(qb[g], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+      }
+      if (ACT != 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = apply_act<ACT>(v[j]);
+      }
+      if (has_scale) {
+        float t[8];
+        unpack8(qs[g], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= t[j];
+      }
+      if (has_res) {
+        float t[8];
+        unpack8(qr[g], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += t[j];
+      }
+      if (ep.out_fp32) {
+        float4* c4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + c_off + col);
+        if (ep.accumulate) {
+          const float4 o0 = c4[0], o1 = c4[1];
+          v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w;
+          v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+        }
+        c4[0] = make_float4(v[0], v[1], v[2], v[3]);
+        c4[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+        bf16* cp = reinterpret_cast<bf16*>(ep.C) + c_off + col;
+        if (ep.accumulate) {
+          float t[8];
+          unpack8(*reinterpret_cast<const uint4*>(cp), t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += t[j];
+        }
+        *reinterpret_cast<uint4*>(cp) = pack8(v);
+      }
+    }
+  }
   }
 }
 
