@@ -139,6 +139,7 @@ class KernelTimer:
 
     def __init__(self):
         self.events = []  # (kind, work, start, end)
+        self.shapes = []  # per GEMM launch: (out shape, K, a_mn, b_mn, act, bias?, residual?, event index)
         self.enabled = False
 
     def wrap(self, ops_mod):
@@ -154,6 +155,8 @@ class KernelTimer:
             e.record()
             K = a.shape[-2] if kw.get("a_mn") else a.shape[-1]
             timer.events.append(("gemm", 2.0 * out.numel() * K, s, e))
+            timer.shapes.append((tuple(out.shape), K, bool(kw.get("a_mn")), bool(kw.get("b_mn")), kw.get("act"),
+                                 kw.get("bias") is not None, kw.get("residual") is not None, len(timer.events) - 1))
             return out
 
         def sva_f(q, ks, vs, masks, rs, batch, q_side, **kw):
@@ -179,6 +182,19 @@ class KernelTimer:
             return r
 
         ops_mod.gemm, ops_mod.sva_window_attn_fwd, ops_mod.sva_window_attn_bwd = gemm, sva_f, sva_b
+
+    def shape_table(self, top=24):
+        """Per-shape GEMM time / rate inside the timed step (CB_BENCH_SHAPES=1 prints it to stderr)."""
+        agg = {}
+        for rec in self.shapes:
+            _, work, s, e = self.events[rec[-1]]
+            a = agg.setdefault(rec[:-1], [0.0, 0.0, 0])
+            a[0] += work
+            a[1] += s.elapsed_time(e)
+            a[2] += 1
+        rows = sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]
+        return [f"{ms:9.2f} ms {n:5d}x {fl / ms / 1e9:7.0f} TF/s  out={k[0]} K={k[1]} a_mn={int(k[2])} b_mn={int(k[3])} "
+                f"act={k[4]} bias={int(k[5])} res={int(k[6])}" for k, (fl, ms, n) in rows]
 
     def totals(self):
         agg = {}
@@ -390,8 +406,10 @@ def main():
     l0 = lib.cb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         loss = step_resident()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1000.0 / args.steps  # CPU time to enqueue one step (no sync)
     e1.record()
     barrier()
     timer.enabled = False
@@ -422,6 +440,8 @@ def main():
     e2e_value = world * B / (ms_e2e / args.steps / 1000.0)
     hbm_peak, tf_sustained, tf_burst, peak_src = peaks()
     agg = timer.totals()
+    if os.environ.get("CB_BENCH_SHAPES"):
+        print("\n".join(timer.shape_table()), file=sys.stderr)
     roof = None
     if "gemm" in agg:
         fl, tms, n = agg["gemm"]
@@ -478,7 +498,7 @@ def main():
                         "parallelism": f"dp{world}", "activation_recompute": bool(args.recompute),
                         "optimizer": "AdamW fp32 master + bf16 grads, fused", "trainable_params": n_train,
                         "frozen_tower_params": n_tower, "l2_policy": "inputs larger than L2 (16 GB weights streamed per pass)"},
-                gpu_launches=int(launches), loss=float(loss),
+                gpu_launches=int(launches), host_enqueue_ms_per_step=round(host_enqueue_ms, 1), loss=float(loss),
                 peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=4),
                 clocks=sampler.summary(), roofline=roof, roofline_sva=roof_sva,

@@ -326,35 +326,55 @@ __global__ void patchify_nhwc_kernel(const bf16* __restrict__ in, bf16* __restri
 // y[b,y,x,c] = bias[c] + sum_{dy,dx} w[dy,dx,c] * x[b, y+dy-3, x+dx-3, c]     (timm ConvNeXtBlock.conv_dw,
 // reached from clip_convnext_encoder.py:121-144).  Weights pre-permuted to [7,7,C].  Each thread owns 8 channels
 // of one output pixel; neighbouring threads share input rows through L1/L2 (bandwidth-bound, 49 taps).
-// Register-tiled version: each thread owns 8 channels of a 2 x 4 patch of output pixels and walks the 8 input rows the
-// patch needs once (10 input vectors per row), so every loaded input vector feeds up to 2 x 7 taps instead of one —
-// 22 vector loads per output instead of 98 (the first, one-output-per-thread version was 5.3% of the training step).
-constexpr int DW_TY = 2, DW_TX = 4;
-__global__ void __launch_bounds__(128)
+// Register-tiled: each thread owns 8 channels of a 2 x 4 patch of output pixels and walks the 8 input rows the patch
+// needs once (10 input vectors per row), so every loaded input vector feeds up to 2 x 7 taps.
+// Block = 16 channel-vectors (128 channels) x 8 patches covering an 8 x 8 pixel region; the block's 49 x 128 weights
+// are converted to fp32 ONCE into shared memory (25 KB) and the block then walks down a column strip, so (a) the
+// per-tap weight fetch is two conflict-free LDS.128 instead of an L2-latency LDG + 8 unpack ops (C = 1536: 150 KB of
+// weights never fit L1 next to the streamed input), (b) vertically adjacent steps re-hit their halo rows in L1.
+constexpr int DW_TY = 2, DW_TX = 4, DW_CV = 16;
+__global__ void __launch_bounds__(128, 3)
 dwconv7_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const bf16* __restrict__ bias,
-               bf16* __restrict__ out, int B, int H, int W, int C) {
+               bf16* __restrict__ out, int B, int H, int W, int C, int ysplit) {
+  // [tap][half][cv][4]: lanes read consecutive 16-byte words (a [cv][8] layout makes LDS.128 2-way bank-conflicted)
+  __shared__ __align__(16) float sw[49][2][DW_CV * 4];
+  __shared__ __align__(16) float sb[DW_CV * 8];
   const int vpr = C >> 3;
-  const int txn = (W + DW_TX - 1) / DW_TX, tyn = (H + DW_TY - 1) / DW_TY;
-  const long long total = (long long)B * tyn * txn * vpr;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % vpr);
-    long long t = i / vpr;
-    const int tx = (int)(t % txn);
-    t /= txn;
-    const int ty = (int)(t % tyn);
-    const int b = (int)(t / tyn);
-    const int x0 = tx * DW_TX, y0 = ty * DW_TY;
+  const int nchunk = (vpr + DW_CV - 1) / DW_CV;
+  const int strips = (W + 7) / 8;
+  int bid = blockIdx.x;
+  const int chunk = bid % nchunk;
+  bid /= nchunk;
+  const int ys = bid % ysplit;
+  bid /= ysplit;
+  const int strip = bid % strips;
+  const int b = bid / strips;
+  const int c_base = chunk * DW_CV * 8;
+  for (int i = threadIdx.x; i < 49 * DW_CV * 8; i += blockDim.x) {
+    const int tap = i / (DW_CV * 8), c = i - tap * (DW_CV * 8);
+    sw[tap][(c >> 2) & 1][(c >> 3) * 4 + (c & 3)] =
+        (c_base + c < C) ? __bfloat162float(w[(long long)tap * C + c_base + c]) : 0.f;
+  }
+  for (int i = threadIdx.x; i < DW_CV * 8; i += blockDim.x)
+    sb[i] = (bias && c_base + i < C) ? __bfloat162float(bias[c_base + i]) : 0.f;
+  __syncthreads();
+  const int cv = threadIdx.x & (DW_CV - 1), st = threadIdx.x / DW_CV;
+  const int v = chunk * DW_CV + cv;
+  if (v >= vpr) return;
+  const int steps = (H + 7) / 8, per = (steps + ysplit - 1) / ysplit;
+  const int s_end = min(steps, (ys + 1) * per);
+  const int x0 = strip * 8 + (st & 1) * DW_TX;
+  if (x0 >= W) return;
+  for (int s = ys * per; s < s_end; ++s) {
+    const int y0 = s * 8 + (st >> 1) * DW_TY;
+    if (y0 >= H) break;
     float acc[DW_TY][DW_TX][8];
-    {
-      float bv[8];
-      if (bias) unpack8(reinterpret_cast<const uint4*>(bias)[v], bv);
 #pragma unroll
-      for (int oy = 0; oy < DW_TY; ++oy)
+    for (int oy = 0; oy < DW_TY; ++oy)
 #pragma unroll
-        for (int ox = 0; ox < DW_TX; ++ox)
+      for (int ox = 0; ox < DW_TX; ++ox)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[oy][ox][e] = bias ? bv[e] : 0.f;
-    }
+        for (int e = 0; e < 8; ++e) acc[oy][ox][e] = sb[cv * 8 + e];
     const bf16* img = in + (long long)b * H * W * C + v * 8;
 #pragma unroll 1
     for (int r = 0; r < DW_TY + 6; ++r) {
@@ -377,8 +397,9 @@ dwconv7_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const bf
         if (ky < 0 || ky > 6) continue;
 #pragma unroll
         for (int kx = 0; kx < 7; ++kx) {
-          float k[8];
-          unpack8(reinterpret_cast<const uint4*>(w + (long long)(ky * 7 + kx) * C)[v], k);
+          const float4 k0 = *reinterpret_cast<const float4*>(&sw[ky * 7 + kx][0][cv * 4]);
+          const float4 k1 = *reinterpret_cast<const float4*>(&sw[ky * 7 + kx][1][cv * 4]);
+          const float k[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
           for (int ox = 0; ox < DW_TX; ++ox)
 #pragma unroll
@@ -743,8 +764,13 @@ int patchify_nhwc_launch(const void* in, void* out, int B, int H, int W, int C, 
 int dwconv7_launch(const void* in, const void* w, const void* bias, void* out, int B, int H, int W, int C,
                    cudaStream_t st) {
   VEC_CHECK(C, "dwconv7");
-  dwconv7_kernel<<<grid_for((long long)B * ((H + DW_TY - 1) / DW_TY) * ((W + DW_TX - 1) / DW_TX) * (C / 8), 128, 16), 128, 0, st>>>((const bf16*)in, (const bf16*)w,
-                                                                                   (const bf16*)bias, (bf16*)out, B, H, W, C);
+  const int nchunk = (C / 8 + DW_CV - 1) / DW_CV, strips = (W + 7) / 8, steps = (H + 7) / 8;
+  const long long base = (long long)nchunk * strips * B;
+  // >= ~4 waves of (SMs x 3 resident blocks) when the image is tall enough, so the tail wave stays small
+  const long long want = (4LL * 3 * device_sm_count() + base - 1) / base;
+  const int ysplit = (int)std::max(1LL, std::min<long long>(steps, want));
+  dwconv7_kernel<<<(unsigned)(base * ysplit), 128, 0, st>>>((const bf16*)in, (const bf16*)w, (const bf16*)bias,
+                                                            (bf16*)out, B, H, W, C, ysplit);
   CB_CUDA_LAUNCH_CHECK("dwconv7");
   return CB_OK;
 }

@@ -235,13 +235,28 @@ def group_elem():
     got = ops.gemm(ops.patchify_nhwc(x, 2), w2.permute(0, 2, 3, 1).reshape(128, -1).contiguous(), out_dtype=torch.float32)
     e2 = rel_err(got, ref)
     print(f"patchify nchw={e1:.2e} nhwc={e2:.2e} {'OK' if max(e1, e2) < 1e-3 else 'FAIL'}", flush=True)
-    # dwconv7
-    x = torch.randn(2, 12, 12, 384, device=dev).bfloat16()
-    w = torch.randn(384, 1, 7, 7, device=dev).bfloat16()
-    b = torch.randn(384, device=dev).bfloat16()
-    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=3, groups=384).permute(0, 2, 3, 1)
-    got = ops.dwconv7(x, w.view(384, 49).t().contiguous().view(7, 7, 384), b)
-    print(f"dwconv7 err={rel_err(got, ref):.2e} {'OK' if rel_err(got, ref) < 1e-2 else 'FAIL'}", flush=True)
+    # dwconv7 (ragged H / W, partial channel chunk, multi-step column strips)
+    for (bb, hh, ww, cc) in ((2, 12, 12, 384), (1, 13, 11, 200), (2, 40, 24, 128), (1, 64, 64, 1536)):
+        x = torch.randn(bb, hh, ww, cc, device=dev).bfloat16()
+        w = torch.randn(cc, 1, 7, 7, device=dev).bfloat16()
+        b = torch.randn(cc, device=dev).bfloat16()
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=3, groups=cc).permute(0, 2, 3, 1)
+        got = ops.dwconv7(x, w.view(cc, 49).t().contiguous().view(7, 7, cc), b)
+        print(f"dwconv7 {bb}x{hh}x{ww}x{cc} err={rel_err(got, ref):.2e} {'OK' if rel_err(got, ref) < 1e-2 else 'FAIL'}", flush=True)
+    x = torch.randn(4, 64, 64, 1536, device=dev).bfloat16()
+    w = torch.randn(7, 7, 1536, device=dev).bfloat16()
+    b = torch.randn(1536, device=dev).bfloat16()
+    for _ in range(3):
+        ops.dwconv7(x, w, b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ops.dwconv7(x, w, b)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    print(f"perf dwconv7 4x64x64x1536: {ms * 1e3:.1f} us  {2 * x.numel() * 2 / ms / 1e6:.0f} GB/s  {x.numel() * 49 * 2 / ms / 1e9:.2f} TFLOP/s fp32", flush=True)
     # reductions
     x = torch.randn(4 * 576, 1024, device=dev).bfloat16()
     e1 = rel_err(ops.group_colsum(x, 4, 1.0 / 576), x.float().view(4, 576, 1024).mean(1))
