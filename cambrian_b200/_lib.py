@@ -56,6 +56,10 @@ SIGNATURES = {
     "cb_adamw": (_i, [_vp] * 5 + [_i64] + [_f] * 5 + [_i, _f, _vp]),
     "cb_span_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "cb_span_scatter": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "cb_span_gather_hw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "cb_span_scatter_hw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "cb_window_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "cb_embed_splice_ragged": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
 }
 
 _lib = None

@@ -83,8 +83,10 @@ int cross_entropy_launch(void*, const long long*, float*, float*, long long, lon
                          long long, cudaStream_t);
 int adamw_launch(float*, float*, float*, const void*, void*, long long, float, float, float, float, float, int, float,
                  cudaStream_t);
-int span_gather_launch(const void*, void*, int, int, int, int, int, cudaStream_t);
-int span_scatter_launch(void*, const void*, int, int, int, int, int, cudaStream_t);
+int span_gather_launch(const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int span_scatter_launch(void*, const void*, int, int, int, int, int, int, cudaStream_t);
+int window_gather_launch(const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
+int embed_splice_ragged_launch(void*, const void*, const void*, const void*, const int*, long long, int, cudaStream_t);
 
 }  // namespace cb
 
@@ -224,10 +226,24 @@ int cb_cross_entropy(void* logits, const int64_t* labels, float* loss_rows, floa
                                   grad_scale, write_grad, ignore_index, ST(stream));
 }
 int cb_span_gather(const void* hidden, void* lat, int B, int S, int H, int start, int q_side, void* stream) {
-  return cb::span_gather_launch(hidden, lat, B, S, H, start, q_side, ST(stream));
+  return cb::span_gather_launch(hidden, lat, B, S, H, start, q_side, q_side, ST(stream));
+}
+int cb_span_gather_hw(const void* hidden, void* lat, int B, int S, int H, int start, int q_h, int q_w, void* stream) {
+  return cb::span_gather_launch(hidden, lat, B, S, H, start, q_h, q_w, ST(stream));
+}
+int cb_span_scatter_hw(void* hidden, const void* lat, int B, int S, int H, int start, int q_h, int q_w, void* stream) {
+  return cb::span_scatter_launch(hidden, lat, B, S, H, start, q_h, q_w, ST(stream));
+}
+int cb_window_gather(const void* feat, void* out, int B, int q_side, int r, int C, int y0, int y1, int x0, int x1,
+                     void* stream) {
+  return cb::window_gather_launch(feat, out, B, q_side, r, C, y0, y1, x0, x1, ST(stream));
+}
+int cb_embed_splice_ragged(void* out, const void* embed, const void* img, const void* newline, const int32_t* src,
+                           int64_t rows, int H, void* stream) {
+  return cb::embed_splice_ragged_launch(out, embed, img, newline, src, rows, H, ST(stream));
 }
 int cb_span_scatter(void* hidden, const void* lat, int B, int S, int H, int start, int q_side, void* stream) {
-  return cb::span_scatter_launch(hidden, lat, B, S, H, start, q_side, ST(stream));
+  return cb::span_scatter_launch(hidden, lat, B, S, H, start, q_side, q_side, ST(stream));
 }
 int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int step, float grad_scale, void* stream) {

@@ -3,6 +3,7 @@
 // All kernels use 16-byte vector accesses on the contiguous channel dimension (C % 8 == 0), fp32 math,
 // grid-stride loops sized in multiples of the SM count.  Reference call sites are cited per kernel.
 #include "common.cuh"
+#include <climits>
 
 namespace cb {
 
@@ -418,6 +419,51 @@ dwconv7_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const bf
   }
 }
 
+// ------------------------------------------------------------------------ dynamic-shape (inference) helpers
+// rearrange_vision_tower_features_inference (cambrian_arch.py:289-330): feat [B, side, side, C] with side = q * r
+// -> windows [B * (y1-y0) * (x1-x0), r*r, C] for the query rows [y0, y1) x columns [x0, x1) (the crop `unpad_image`
+// applies to the q x q window grid; full range = the train-time rearrangement :271-287).
+__global__ void window_gather_kernel(const bf16* __restrict__ feat, bf16* __restrict__ out, int B, int q, int r, int C,
+                                     int y0, int y1, int x0, int x1) {
+  const int vpr = C >> 3;
+  const int hh = y1 - y0, ww = x1 - x0, side = q * r;
+  const long long total = (long long)B * hh * ww * r * r * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpr);
+    long long t = i / vpr;
+    const int wx = (int)(t % r);
+    t /= r;
+    const int wy = (int)(t % r);
+    t /= r;
+    const int qx = (int)(t % ww) + x0;
+    t /= ww;
+    const int qy = (int)(t % hh) + y0;
+    const int b = (int)(t / hh);
+    const long long src = (((long long)b * side + qy * r + wy) * side + qx * r + wx) * C;
+    reinterpret_cast<uint4*>(out)[i] = ldg_nc(reinterpret_cast<const uint4*>(feat + src) + v);
+  }
+}
+
+// Ragged embedding + image splice (cambrian_arch.py:493-609): out[row] = embed[src] (src >= 0) | zeros (src == -1,
+// padding) | newline (src == INT_MIN) | img[-2 - src] (image feature row).  The row map is built on the host from the
+// ids, attention mask and per-sample unpadded grid sizes.
+__global__ void embed_splice_ragged_kernel(bf16* __restrict__ out, const bf16* __restrict__ embed,
+                                           const bf16* __restrict__ img, const bf16* __restrict__ newline,
+                                           const int* __restrict__ src, long long rows, int H) {
+  const int vpr = H >> 3;
+  const long long total = rows * vpr;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpr);
+    const long long row = i / vpr;
+    const int s = src[row];
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (s >= 0) val = ldg_nc(reinterpret_cast<const uint4*>(embed + (long long)s * H) + v);
+    else if (s == INT_MIN) val = ldg_nc(reinterpret_cast<const uint4*>(newline) + v);
+    else if (s <= -2) val = ldg_nc(reinterpret_cast<const uint4*>(img + (long long)(-2 - s) * H) + v);
+    reinterpret_cast<uint4*>(out)[i] = val;
+  }
+}
+
 // ---------------------------------------------------------------------------- small reductions
 // dst += src (bf16), used where a tensor feeds several consumers in hand-written backward passes
 __global__ void add_inplace_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, long long nvec) {
@@ -512,31 +558,31 @@ __global__ void f32_to_bf16_kernel(const float4* __restrict__ in, bf16* __restri
 // stream hold q rows of (q latent queries + 1 newline token).  gather copies the q*q latent rows into a dense
 // [B*q*q, H] buffer; scatter writes (updated) latent rows back in place.  Newline rows are never touched.
 __global__ void span_gather_kernel(const bf16* __restrict__ hidden, bf16* __restrict__ lat, int B, int S, int H, int start,
-                                   int q_side) {
+                                   int q_h, int q_side) {
   const int vpr = H >> 3;
-  const long long total = (long long)B * q_side * q_side * vpr;
+  const long long total = (long long)B * q_h * q_side * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % vpr);
     long long t = i / vpr;
     const int col = (int)(t % q_side);
     t /= q_side;
-    const int row = (int)(t % q_side);
-    const int b = (int)(t / q_side);
+    const int row = (int)(t % q_h);
+    const int b = (int)(t / q_h);
     const long long src = ((long long)b * S + start + row * (q_side + 1) + col) * H;
     reinterpret_cast<uint4*>(lat)[i] = ldg_nc(reinterpret_cast<const uint4*>(hidden + src) + v);
   }
 }
 __global__ void span_scatter_kernel(bf16* __restrict__ hidden, const bf16* __restrict__ lat, int B, int S, int H, int start,
-                                    int q_side) {
+                                    int q_h, int q_side) {
   const int vpr = H >> 3;
-  const long long total = (long long)B * q_side * q_side * vpr;
+  const long long total = (long long)B * q_h * q_side * vpr;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % vpr);
     long long t = i / vpr;
     const int col = (int)(t % q_side);
     t /= q_side;
-    const int row = (int)(t % q_side);
-    const int b = (int)(t / q_side);
+    const int row = (int)(t % q_h);
+    const int b = (int)(t / q_h);
     const long long dst = ((long long)b * S + start + row * (q_side + 1) + col) * H;
     reinterpret_cast<uint4*>(hidden + dst)[v] = ldg_nc(reinterpret_cast<const uint4*>(lat) + i);
   }
@@ -814,21 +860,40 @@ int f32_to_bf16_launch(const float* in, void* out, long long rows, int cols, lon
   CB_CUDA_LAUNCH_CHECK("f32_to_bf16");
   return CB_OK;
 }
-int span_gather_launch(const void* hidden, void* lat, int B, int S, int H, int start, int q_side, cudaStream_t st) {
+int window_gather_launch(const void* feat, void* out, int B, int q, int r, int C, int y0, int y1, int x0, int x1,
+                         cudaStream_t st) {
+  VEC_CHECK(C, "window_gather");
+  CB_CHECK_ARG(q > 0 && r > 0 && 0 <= y0 && y0 < y1 && y1 <= q && 0 <= x0 && x0 < x1 && x1 <= q,
+               "window_gather: crop [%d,%d)x[%d,%d) outside the %dx%d query grid", y0, y1, x0, x1, q, q);
+  window_gather_kernel<<<grid_for((long long)B * (y1 - y0) * (x1 - x0) * r * r * (C / 8), 256), 256, 0, st>>>(
+      (const bf16*)feat, (bf16*)out, B, q, r, C, y0, y1, x0, x1);
+  CB_CUDA_LAUNCH_CHECK("window_gather");
+  return CB_OK;
+}
+int embed_splice_ragged_launch(void* out, const void* embed, const void* img, const void* newline, const int* src,
+                               long long rows, int H, cudaStream_t st) {
+  VEC_CHECK(H, "embed_splice_ragged");
+  CB_CHECK_ARG(rows > 0, "embed_splice_ragged: no rows");
+  embed_splice_ragged_kernel<<<grid_for(rows * (H / 8), 256), 256, 0, st>>>((bf16*)out, (const bf16*)embed, (const bf16*)img,
+                                                                          (const bf16*)newline, src, rows, H);
+  CB_CUDA_LAUNCH_CHECK("embed_splice_ragged");
+  return CB_OK;
+}
+int span_gather_launch(const void* hidden, void* lat, int B, int S, int H, int start, int q_h, int q_side, cudaStream_t st) {
   VEC_CHECK(H, "span_gather");
-  CB_CHECK_ARG(start >= 0 && start + q_side * (q_side + 1) <= S, "span_gather: image span [%d, +%d) outside sequence %d",
-               start, q_side * (q_side + 1), S);
-  span_gather_kernel<<<grid_for((long long)B * q_side * q_side * (H / 8), 256), 256, 0, st>>>((const bf16*)hidden, (bf16*)lat,
-                                                                                            B, S, H, start, q_side);
+  CB_CHECK_ARG(q_h > 0 && q_side > 0 && start >= 0 && start + q_h * (q_side + 1) <= S,
+               "span_gather: image span [%d, +%d) outside sequence %d", start, q_h * (q_side + 1), S);
+  span_gather_kernel<<<grid_for((long long)B * q_h * q_side * (H / 8), 256), 256, 0, st>>>((const bf16*)hidden, (bf16*)lat,
+                                                                                         B, S, H, start, q_h, q_side);
   CB_CUDA_LAUNCH_CHECK("span_gather");
   return CB_OK;
 }
-int span_scatter_launch(void* hidden, const void* lat, int B, int S, int H, int start, int q_side, cudaStream_t st) {
+int span_scatter_launch(void* hidden, const void* lat, int B, int S, int H, int start, int q_h, int q_side, cudaStream_t st) {
   VEC_CHECK(H, "span_scatter");
-  CB_CHECK_ARG(start >= 0 && start + q_side * (q_side + 1) <= S, "span_scatter: image span [%d, +%d) outside sequence %d",
-               start, q_side * (q_side + 1), S);
-  span_scatter_kernel<<<grid_for((long long)B * q_side * q_side * (H / 8), 256), 256, 0, st>>>((bf16*)hidden, (const bf16*)lat,
-                                                                                             B, S, H, start, q_side);
+  CB_CHECK_ARG(q_h > 0 && q_side > 0 && start >= 0 && start + q_h * (q_side + 1) <= S,
+               "span_scatter: image span [%d, +%d) outside sequence %d", start, q_h * (q_side + 1), S);
+  span_scatter_kernel<<<grid_for((long long)B * q_h * q_side * (H / 8), 256), 256, 0, st>>>((bf16*)hidden, (const bf16*)lat,
+                                                                                          B, S, H, start, q_h, q_side);
   CB_CUDA_LAUNCH_CHECK("span_scatter");
   return CB_OK;
 }

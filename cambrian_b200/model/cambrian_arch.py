@@ -10,9 +10,10 @@ Differences that are purely layout, not semantics:
   * the per-query window gather (`rearrange_vision_tower_features_train`, :271-287) is NOT materialised: the aux
     feature grids stay in their natural [B, N_i, 1024] layout and the SVA kernels do the index arithmetic;
   * embedding lookup + image-span replacement + newline append are one gather kernel (`EmbedSpliceFn`).
-The per-sample dynamic-shape branch (non-square `image_sizes`, :289-330, :422-451, :493-609) is the next row of
-SURVEY.md §8f and raises NotImplementedError for non-square images; square images give identical results on both
-branches.
+The per-sample dynamic-shape branch the reference runs off-XLA (:289-330, :422-451, :493-609) is
+`_prepare_dynamic`: taken when `image_sizes` holds a non-square image (square images give identical results on both
+branches), inference only.  There the windows ARE materialised (`cb_window_gather`, with the `unpad_image` crop) because
+the per-sample query counts differ, and the ragged splice is one gather kernel driven by a host-built row map.
 """
 from __future__ import annotations
 
@@ -21,6 +22,7 @@ from abc import ABC, abstractmethod
 import torch
 import torch.nn as nn
 
+from .. import ops
 from ..autograd import EmbedSpliceFn, ExpandRowsFn, MeanTokensFn
 from .multimodal_encoder.builder import build_vision_tower_aux_list
 from .multimodal_projector.builder import CBGELU, CBLayerNorm, CBLinear, build_vision_projector
@@ -95,6 +97,62 @@ class CambrianMetaModel:
         self._build_vision_modules(cfg, delay_load=False)
 
 
+class WindowedFeatures(list):
+    """Marks a list of tower features as ALREADY window-rearranged ([sum_b h_b*w_b, r_i^2, C], the layout the
+    reference's non-XLA branch hands to the decoder loop) as opposed to the natural [B, N_i, C] grids the static
+    branch keeps."""
+
+
+def unmask_attention_mask(mask, original_size):
+    """cambrian_arch.py:203-227 — zero the letter-box band of a [1, h, w] mask (in place), host tensor."""
+    original_w, original_h = original_size
+    cur_h, cur_w = mask.shape[1:3]
+    if original_w / original_h > cur_w / cur_h:
+        new_height = int(original_h * (cur_w / original_w))
+        padding = (cur_h - new_height) // 2
+        if padding > 0:
+            mask[:, :padding, :] = 0
+            mask[:, -padding:, :] = 0
+    else:
+        new_width = int(original_w * (cur_h / original_h))
+        padding = (cur_w - new_width) // 2
+        if padding > 0:
+            mask[:, :, :padding] = 0
+            mask[:, :, -padding:] = 0
+    return mask
+
+
+def unpad_bounds(cur_h, cur_w, original_size):
+    """The crop `unpad_image` (cambrian_arch.py:230-256) applies to dims (1, 2) of its argument: (y0, y1, x0, x1)."""
+    original_w, original_h = original_size
+    if original_w / original_h > cur_w / cur_h:
+        new_height = int(original_h * (cur_w / original_w))
+        padding = (cur_h - new_height) // 2
+        return padding, cur_h - padding, 0, cur_w
+    new_width = int(original_w * (cur_h / original_h))
+    padding = (cur_w - new_width) // 2
+    return 0, cur_h, padding, cur_w - padding
+
+
+def unpad_image(tensor, original_size):
+    """cambrian_arch.py:230-256 (any tensor whose dims 1, 2 are the padded grid)."""
+    y0, y1, x0, x1 = unpad_bounds(tensor.shape[1], tensor.shape[2], original_size)
+    return tensor[:, y0:y1, x0:x1]
+
+
+def _window_masks_inference(aux_side, q_side, image_size, unpad):
+    """Host part of rearrange_vision_tower_features_inference (cambrian_arch.py:306-320) for one sample."""
+    r = aux_side // q_side
+    m = torch.ones((1, aux_side, aux_side), dtype=torch.bool)
+    m = unmask_attention_mask(m, image_size)
+    m = m.view(1, q_side, r, q_side, r).permute(0, 1, 3, 2, 4).contiguous()
+    if unpad:
+        m = unpad_image(m, image_size)
+    m = m.flatten(0, 2).flatten(1, 2).clone()
+    m[m.sum(-1) == 0] = True
+    return m
+
+
 class CambrianMetaForCausalLM(ABC):
     @abstractmethod
     def get_model(self):
@@ -106,6 +164,137 @@ class CambrianMetaForCausalLM(ABC):
     def encode_images(self, image_aux_list):
         """cambrian_arch.py:332-338."""
         return [tower(img) for img, tower in zip(image_aux_list, self.get_model().get_vision_tower_aux_list())]
+
+    def rearrange_vision_tower_features_train(self, vision_tower_aux_feature_list, vision_tower_aux_attention_masks_list,
+                                              query_side_len):
+        """cambrian_arch.py:271-287: [B, (q r)^2, C] -> [B q^2, r^2, C]; masks -> [B q^2, r^2]."""
+        feats, masks = [], []
+        for f, m in zip(vision_tower_aux_feature_list, vision_tower_aux_attention_masks_list):
+            w = ops.window_gather(f.to(torch.bfloat16).contiguous(), query_side_len)
+            feats.append(w)
+            masks.append(m.view(w.shape[0], w.shape[1]))
+        return feats, masks
+
+    def rearrange_vision_tower_features_inference(self, vision_tower_aux_feature_list, query_side_len, image_sizes,
+                                                  unpad=False):
+        """cambrian_arch.py:289-330: per-sample windows (+ the `unpad_image` crop of the q x q window grid) and the
+        letter-box masks derived from the ORIGINAL image sizes; samples are concatenated along dim 0 (ragged)."""
+        feats, masks = WindowedFeatures(), []
+        bs = vision_tower_aux_feature_list[0].shape[0]
+        for f in vision_tower_aux_feature_list:
+            f = f.to(torch.bfloat16).contiguous()
+            aux_side = int(f.shape[1] ** 0.5)
+            assert (aux_side // query_side_len) * query_side_len == aux_side                       # :296
+            fw, mw = [], []
+            for b in range(bs):
+                crop = unpad_bounds(query_side_len, query_side_len, image_sizes[b]) if unpad else None
+                fw.append(ops.window_gather(f[b:b + 1], query_side_len, crop))
+                mw.append(_window_masks_inference(aux_side, query_side_len, image_sizes[b], unpad))
+            feats.append(fw[0] if bs == 1 else torch.cat(fw, 0))
+            masks.append(torch.cat(mw, 0).to(f.device, non_blocking=True))
+        return feats, masks
+
+    def _prepare_dynamic(self, input_ids, position_ids, attention_mask, past_key_values, labels, images, image_sizes):
+        """The reference's non-XLA branch (cambrian_arch.py:387-389, :422-451, :493-609): per-sample unpadded query
+        grids for non-square images.  Inference only (no backward through the gather kernels)."""
+        model = self.get_model()
+        cfg = model.config
+        if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
+            raise NotImplementedError("the dynamic-shape (non-square image) branch is inference-only: run under torch.no_grad()")
+        bs = images[0].shape[0]
+        q_num = cfg.image_token_len
+        fh = fw = int(q_num ** 0.5)
+        feats = self.encode_images(images)
+        feats_final = masks_final = ctx_final = None
+        if cfg.mm_projector_type == "sva":
+            aux = [getattr(model, f"mm_projector_aux_{i}")(f.to(torch.bfloat16)) for i, f in enumerate(feats)]
+            ctx = MeanTokensFn.apply(aux[0])                                                     # [B, vh]
+            outs = []
+            for g, query_num in enumerate(cfg.query_num_list):
+                qs = int(query_num ** 0.5)
+                n = bs * query_num
+                queries = ExpandRowsFn.apply(model.vision_query[g:g + 1].to(torch.bfloat16), n)
+                ctx_g = ExpandRowsFn.apply(ctx, query_num)
+                f_i, m_i = self.rearrange_vision_tower_features_inference(aux, qs, image_sizes)     # :389
+                qf = getattr(model, f"vision_sampler_{g}")(queries.view(n, 1, -1), ctx_g.view(n, 1, -1), *f_i, *m_i)
+                if qs != fh:
+                    raise NotImplementedError("query groups with a side different from the final grid "
+                                              "(cambrian_arch.py:394-401)")
+                outs.append(qf.view(bs, query_num, -1))
+            image_features = outs[0] if len(outs) == 1 else torch.cat(outs, -1)
+            feats_final, masks_final = self.rearrange_vision_tower_features_inference(aux, fh, image_sizes, unpad=True)
+        else:
+            image_features = (feats[0] if len(feats) == 1 else torch.cat(feats, -1)).to(torch.bfloat16)
+        image_features = model.mm_projector(image_features).contiguous()                          # [bs, fh*fw, H]
+        bounds = [unpad_bounds(fh, fw, image_sizes[b]) for b in range(bs)]
+        final_size = [(y1 - y0, x1 - x0) for (y0, y1, x0, x1) in bounds]
+        if cfg.mm_projector_type == "sva":
+            ctx_final = torch.cat([ExpandRowsFn.apply(ctx[b:b + 1], h * w) for b, (h, w) in enumerate(final_size)], 0)
+            ctx_final = ctx_final.view(-1, 1, ctx.shape[-1])
+        # ---- ragged splice, host side (cambrian_arch.py:493-609) -> one row map for the gather kernel
+        NEWLINE = -(2 ** 31)
+        dev = input_ids.device
+        ids_cpu = input_ids.detach().to("cpu")
+        _labels, _position_ids, _attention_mask = labels, position_ids, attention_mask
+        am = torch.ones_like(ids_cpu, dtype=torch.bool) if attention_mask is None else attention_mask.detach().to("cpu").bool()
+        lab_cpu = torch.full_like(ids_cpu, IGNORE_INDEX) if labels is None else labels.detach().to("cpu")
+        rows_src, rows_lab = [], []
+        cur_image_idx = 0
+
+        def image_rows(k):
+            y0, y1, x0, x1 = bounds[k]
+            r = []
+            for y in range(y0, y1):
+                r.extend(-2 - (k * fh * fw + y * fw + x) for x in range(x0, x1))
+                r.append(NEWLINE)
+            return r
+
+        for b in range(bs):
+            cur = ids_cpu[b][am[b]].tolist()
+            cl = lab_cpu[b][am[b]].tolist()
+            src, lab = [], []
+            if IMAGE_TOKEN_INDEX not in cur:
+                cur_image_idx += 1                                                                  # :519-526
+                rows_src.append(cur)
+                rows_lab.append(cl)
+                continue
+            for t, l in zip(cur, cl):
+                if t == IMAGE_TOKEN_INDEX:
+                    ir = image_rows(cur_image_idx)
+                    cur_image_idx += 1
+                    src.extend(ir)
+                    lab.extend([IGNORE_INDEX] * len(ir))
+                else:
+                    src.append(t)
+                    lab.append(l)
+            rows_src.append(src)
+            rows_lab.append(lab)
+        max_tok = getattr(cfg, "tokenizer_model_max_length", None)
+        if max_tok is not None:
+            rows_src = [r[:max_tok] for r in rows_src]
+            rows_lab = [r[:max_tok] for r in rows_lab]
+        max_len = max(len(r) for r in rows_src)
+        left = getattr(cfg, "tokenizer_padding_side", "right") == "left"
+        src_map = torch.full((bs, max_len), -1, dtype=torch.int32)
+        new_labels = torch.full((bs, max_len), IGNORE_INDEX, dtype=lab_cpu.dtype)
+        new_mask = torch.zeros((bs, max_len), dtype=torch.bool)
+        new_pos = torch.zeros((bs, max_len), dtype=torch.long)
+        for b, (r, l) in enumerate(zip(rows_src, rows_lab)):
+            n = len(r)
+            if n == 0:
+                continue
+            sl = slice(max_len - n, max_len) if left else slice(0, n)
+            src_map[b, sl] = torch.tensor(r, dtype=torch.int32)
+            new_labels[b, sl] = torch.tensor(l, dtype=lab_cpu.dtype)
+            new_mask[b, sl] = True
+            new_pos[b, sl] = torch.arange(n)
+        new_embeds = ops.embed_splice_ragged(model.embed_tokens.weight, image_features.view(-1, image_features.shape[-1]),
+                                             model.image_newline, src_map.view(-1).to(dev), bs, max_len)
+        new_labels = None if _labels is None else new_labels.to(dev)
+        out_mask = None if _attention_mask is None else new_mask.to(dev).to(_attention_mask.dtype)
+        out_pos = None if _position_ids is None else new_pos.to(dev)
+        return (None, out_pos, out_mask, past_key_values, new_embeds, new_labels, feats_final, masks_final, final_size,
+                ctx_final)
 
     def prepare_inputs_labels_for_multimodal(self, input_ids, position_ids, attention_mask, past_key_values, labels,
                                              images, image_aux_attention_masks_list=None, image_sizes=None,
@@ -121,8 +310,9 @@ class CambrianMetaForCausalLM(ABC):
         q_num = cfg.image_token_len
         q_side = int(q_num ** 0.5)
         if image_sizes is not None and any(int(w) != int(h) for (w, h) in image_sizes):
-            raise NotImplementedError("non-square image_sizes need the per-sample dynamic branch "
-                                      "(cambrian_arch.py:289-330,:422-451) — SURVEY.md §8f rank 3")
+            # per-sample unpadded grids: the reference's non-XLA branch (for square images it reduces to the static one)
+            return self._prepare_dynamic(input_ids, position_ids, attention_mask, past_key_values, labels, images,
+                                         image_sizes)
         span = q_num + q_side
         # --- locate the image span of every sample; expand a bare <image> indicator the way the collator does
         #     (train_fsdp.py:1089-1165) when the caller passes un-expanded ids (inference path)

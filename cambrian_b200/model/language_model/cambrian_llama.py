@@ -22,7 +22,7 @@ from transformers.modeling_outputs import BaseModelOutputWithPast, CausalLMOutpu
 
 from ... import ops
 from ...autograd import DecoderLayerFn, LinearFn, LMHeadLossFn, RMSNormFn, SpanMergeFn, SpanSplitFn
-from ..cambrian_arch import IGNORE_INDEX, CambrianMetaForCausalLM, CambrianMetaModel
+from ..cambrian_arch import IGNORE_INDEX, CambrianMetaForCausalLM, CambrianMetaModel, WindowedFeatures
 
 
 class CambrianConfig(LlamaConfig):
@@ -298,7 +298,25 @@ class CambrianLlamaModel(CambrianMetaModel, CBLlamaModel):
             if output_hidden_states:
                 all_hidden += (hidden,)
             hidden = layer.infer(hidden, rt, cache) if cache is not None else layer(hidden, rt)
-            if i in sites:
+            if i in sites and isinstance(vision_tower_aux_feature_list, WindowedFeatures):
+                # per-sample unpadded query grids (cambrian_llama.py:208-253), inference only: the latent queries of
+                # every sample are gathered into one ragged batch, updated by the SVA layer, scattered back in place
+                if torch.is_grad_enabled() and hidden.requires_grad:
+                    raise NotImplementedError("the dynamic-shape SVA branch is inference-only")
+                start = cfg.image_position
+                sizes = [(int(h), int(w)) for (h, w) in final_vision_feature_size]
+                lats = [ops.span_gather_hw(hidden[b:b + 1], start, h, w) for b, (h, w) in enumerate(sizes)]
+                lat = lats[0] if len(lats) == 1 else torch.cat(lats, 0)
+                feats = [f.to(lat.dtype) for f in vision_tower_aux_feature_list]
+                masks = vision_tower_aux_attention_masks_list or [None] * len(feats)
+                lat = self.vision_sampler_layers[sites.index(i)](
+                    lat.view(lat.shape[0], 1, H), global_context_feature, *feats, *masks)
+                lat = lat.view(-1, H)
+                o = 0
+                for b, (h, w) in enumerate(sizes):
+                    ops.span_scatter_hw_(hidden[b:b + 1], lat[o:o + h * w], start, h, w)
+                    o += h * w
+            elif i in sites:
                 start = cfg.image_position                                                      # :175
                 n = B * q_num
                 lat, hidden = SpanSplitFn.apply(hidden, start, q_side)

@@ -24,6 +24,12 @@ def _require_cuda_bf16(*ts):
             raise ValueError(f"expected bf16 tensor, got {t.dtype}")
 
 
+def _chk(t, name):
+    _require_cuda_bf16(t)
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
 def workspace(nfloats: int, device) -> torch.Tensor:
     key = (device, torch.cuda.current_stream(device).cuda_stream)
     w = _ws_cache.get(key)
@@ -433,3 +439,54 @@ def span_scatter_(hidden, lat, start: int, q_side: int):
     B, S, H = hidden.shape
     check(_lib.load().cb_span_scatter(ptr(hidden), ptr(lat), B, S, H, start, q_side, stream()), "cb_span_scatter")
     return hidden
+
+
+def span_gather_hw(hidden, start: int, q_h: int, q_w: int):
+    """Dynamic branch (cambrian_llama.py:208-253): q_h rows of (q_w latent queries + 1 newline) -> [B*q_h*q_w, H]."""
+    B, S, H = hidden.shape
+    _chk(hidden, "hidden")
+    lat = torch.empty((B * q_h * q_w, H), dtype=torch.bfloat16, device=hidden.device)
+    check(_lib.load().cb_span_gather_hw(ptr(hidden), ptr(lat), B, S, H, start, q_h, q_w, stream()), "cb_span_gather_hw")
+    return lat
+
+
+def span_scatter_hw_(hidden, lat, start: int, q_h: int, q_w: int):
+    B, S, H = hidden.shape
+    _chk(hidden, "hidden")
+    _chk(lat, "lat")
+    if lat.numel() != B * q_h * q_w * H:
+        raise ValueError("span_scatter_hw_: lat has the wrong number of rows")
+    check(_lib.load().cb_span_scatter_hw(ptr(hidden), ptr(lat), B, S, H, start, q_h, q_w, stream()), "cb_span_scatter_hw")
+    return hidden
+
+
+def window_gather(feat, q_side: int, crop=None):
+    """feat [B, (q r)^2, C] (natural row-major grid) -> [B*h*w, r*r, C] windows of the query rows/cols in
+    crop = (y0, y1, x0, x1) (default: the whole q x q grid) — cambrian_arch.py:271-330."""
+    _chk(feat, "feat")
+    B, N, Cc = feat.shape
+    side = int(round(N ** 0.5))
+    if side * side != N or side % q_side != 0:
+        raise AssertionError("window_gather: token grid is not a square multiple of the query grid")   # :277
+    r = side // q_side
+    y0, y1, x0, x1 = crop if crop is not None else (0, q_side, 0, q_side)
+    out = torch.empty((B * (y1 - y0) * (x1 - x0), r * r, Cc), dtype=torch.bfloat16, device=feat.device)
+    check(_lib.load().cb_window_gather(ptr(feat), ptr(out), B, q_side, r, Cc, y0, y1, x0, x1, stream()), "cb_window_gather")
+    return out
+
+
+def embed_splice_ragged(embed_w, img, newline, src, batch: int, max_len: int):
+    """src: int32 [batch*max_len] row map (>=0 token id, -1 zeros, INT32_MIN newline, <=-2 image row -2-src)."""
+    _chk(embed_w, "embed_w")
+    H = embed_w.shape[1]
+    if src.dtype != torch.int32 or src.numel() != batch * max_len or not src.is_contiguous():
+        raise ValueError("embed_splice_ragged: src must be contiguous int32 [batch*max_len]")
+    if img is not None:
+        _chk(img, "img")
+    if newline is not None:
+        _chk(newline, "newline")
+    out = torch.empty((batch, max_len, H), dtype=torch.bfloat16, device=embed_w.device)
+    check(_lib.load().cb_embed_splice_ragged(ptr(out), ptr(embed_w), ptr(img) if img is not None else None,
+                                             ptr(newline) if newline is not None else None, ptr(src), batch * max_len, H,
+                                             stream()), "cb_embed_splice_ragged")
+    return out

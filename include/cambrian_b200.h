@@ -166,6 +166,19 @@ int cb_cross_entropy(void* logits, const int64_t* labels, float* loss_rows, floa
  * of hidden [B,S,H] into lat [B*q*q, H] / scatter updated rows back in place (newline rows untouched) */
 int cb_span_gather(const void* hidden, void* lat, int B, int S, int H, int start, int q_side, void* stream);
 int cb_span_scatter(void* hidden, const void* lat, int B, int S, int H, int start, int q_side, void* stream);
+/* Dynamic-shape (per-sample, non-square) variant of the two above: the span holds q_h rows of (q_w queries + 1 newline)
+ * (cambrian_llama.py:208-253, final_vision_feature_size[b] = (q_h, q_w)). */
+int cb_span_gather_hw(const void* hidden, void* lat, int B, int S, int H, int start, int q_h, int q_w, void* stream);
+int cb_span_scatter_hw(void* hidden, const void* lat, int B, int S, int H, int start, int q_h, int q_w, void* stream);
+/* Window rearrangement with the `unpad_image` crop of the q x q window grid
+ * (rearrange_vision_tower_features_inference, cambrian_arch.py:289-330; full range = _train, :271-287):
+ * feat [B, q*r, q*r, C] -> out [B*(y1-y0)*(x1-x0), r*r, C] for query rows [y0,y1) x columns [x0,x1). */
+int cb_window_gather(const void* feat, void* out, int B, int q_side, int r, int C, int y0, int y1, int x0, int x1,
+                     void* stream);
+/* Ragged embed + splice of the dynamic branch (cambrian_arch.py:493-609): out[row] = embed[src[row]] if src >= 0,
+ * zeros if src == -1 (padding), newline if src == INT32_MIN, img[-2 - src] otherwise; rows = B * max_len. */
+int cb_embed_splice_ragged(void* out, const void* embed, const void* img, const void* newline, const int32_t* src,
+                           int64_t rows, int H, void* stream);
 /* AdamW on fp32 master weights / moments with bf16 gradients, writing the bf16 compute copy */
 int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int step, float grad_scale, void* stream);

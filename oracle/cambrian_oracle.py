@@ -7,7 +7,8 @@ cpu_baseline / `--impl reference` leg may import it; the product (`cambrian_b200
 Every function takes tensors plus a flat state dict that uses the REFERENCE's parameter names (SURVEY.md §8b
 "State-dict keys"), so the same weights can be loaded into the reference modules, this oracle and the CUDA
 modules.  Pinning status (see tests/test_oracle_pin.py, tests/golden/make_golden.py):
-  * SVA layer / sampler, window rearrange, projectors, connector + splice  — pinned against the reference's own
+  * SVA layer / sampler, window rearrange (train and inference/unpad variants, unmask_attention_mask, unpad_image),
+    projectors, connector + splice — pinned against the reference's own
     modules imported through oracle/ref_shim.py, and against committed golden fixtures generated from them.
   * CLIP ViT, DINOv2 ViT, LLaMA decoder layer — pinned against the installed `transformers` implementations
     the reference delegates to (clip_encoder.py:47, dino_encoder.py:81, cambrian_llama.py:23-24).
@@ -224,6 +225,141 @@ def lm_loss(sd, hidden, labels):
         loss = F.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), labels[:, 1:].reshape(-1),
                                ignore_index=IGNORE_INDEX)
     return logits, loss
+
+
+# ------------------------------------------------------------------------------------------------
+# dynamic-shape (non-XLA / inference) branch: per-sample unpadded query grids
+# ------------------------------------------------------------------------------------------------
+def unmask_attention_mask(mask, original_size):
+    """cambrian_arch.py:203-227."""
+    ow, oh = original_size
+    ch, cw = mask.shape[1:3]
+    if ow / oh > cw / ch:
+        pad = (ch - int(oh * (cw / ow))) // 2
+        if pad > 0:
+            mask[:, :pad, :] = 0
+            mask[:, -pad:, :] = 0
+    else:
+        pad = (cw - int(ow * (ch / oh))) // 2
+        if pad > 0:
+            mask[:, :, :pad] = 0
+            mask[:, :, -pad:] = 0
+    return mask
+
+
+def unpad_image(t, original_size):
+    """cambrian_arch.py:230-256 (crop of dims 1, 2)."""
+    ow, oh = original_size
+    ch, cw = t.shape[1:3]
+    if ow / oh > cw / ch:
+        pad = (ch - int(oh * (cw / ow))) // 2
+        return t[:, pad:ch - pad, :]
+    pad = (cw - int(ow * (ch / oh))) // 2
+    return t[:, :, pad:cw - pad]
+
+
+def rearrange_inference(feats, q_side, image_sizes, unpad=False):
+    """rearrange_vision_tower_features_inference, cambrian_arch.py:289-330."""
+    out_f, out_m = [], []
+    for f in feats:
+        B, N, C = f.shape
+        side = int(N ** 0.5)
+        r = side // q_side
+        fl, ml = [], []
+        for b in range(B):
+            w = f[b].view(1, q_side, r, q_side, r, C).permute(0, 1, 3, 2, 4, 5).contiguous()
+            m = unmask_attention_mask(torch.ones((1, side, side), dtype=torch.bool), image_sizes[b])
+            m = m.view(1, q_side, r, q_side, r).permute(0, 1, 3, 2, 4).contiguous()
+            if unpad:
+                w, m = unpad_image(w, image_sizes[b]), unpad_image(m, image_sizes[b])
+            w = w.flatten(0, 2).flatten(1, 2)
+            m = m.flatten(0, 2).flatten(1, 2).clone()
+            m[m.sum(-1) == 0] = True
+            fl.append(w)
+            ml.append(m)
+        out_f.append(torch.cat(fl, 0))
+        out_m.append(torch.cat(ml, 0))
+    return out_f, out_m
+
+
+def prepare_dynamic(sd, cfg, tower_feats, input_ids, attention_mask, labels, image_sizes):
+    """prepare_inputs_labels_for_multimodal off-XLA (cambrian_arch.py:387-389, :422-451, :493-609), SVA projector, one
+    query group, right padding.  Returns (inputs_embeds, labels, attention_mask, position_ids, feats_final, masks_final,
+    final_size, ctx_final)."""
+    B = tower_feats[0].shape[0]
+    q_num = cfg["image_token_len"]
+    side = int(q_num ** 0.5)
+    aux = [mm_projector_aux(sd, f"model.mm_projector_aux_{i}.", f) for i, f in enumerate(tower_feats)]
+    ctx = aux[0].mean(1).view(B, 1, 1, -1)
+    f_w, m_w = rearrange_inference(aux, side, image_sizes)
+    queries = sd["model.vision_query"][0].view(1, 1, 1, -1).expand(B, q_num, -1, -1).flatten(0, 1)
+    ctx_q = ctx.expand(-1, q_num, 1, -1).flatten(0, 1)
+    qf = sva_sampler(sd, "model.vision_sampler_0.", queries, ctx_q, f_w, m_w, cfg["connector_depth"])
+    img = mlp2x_gelu(sd, "model.mm_projector.", qf.view(B, q_num, -1)).view(B, side, side, -1)
+    feats_final, masks_final = rearrange_inference(aux, side, image_sizes, unpad=True)
+    per_sample, final_size, ctx_final = [], [], []
+    for b in range(B):
+        cur = unpad_image(img[b].unsqueeze(0), image_sizes[b])
+        h, w = cur.shape[1:3]
+        final_size.append((h, w))
+        nl = sd["model.image_newline"].view(1, 1, 1, -1).expand(1, h, 1, -1)
+        per_sample.append(torch.cat([cur, nl], 2).flatten(1, 2).squeeze(0))
+        ctx_final.append(ctx[b].expand(h * w, 1, -1))
+    ctx_final = torch.cat(ctx_final, 0)
+    am = torch.ones_like(input_ids, dtype=torch.bool) if attention_mask is None else attention_mask.bool()
+    lab = torch.full_like(input_ids, IGNORE_INDEX) if labels is None else labels
+    embeds, new_labels = [], []
+    for b in range(B):
+        ids, lb = input_ids[b][am[b]], lab[b][am[b]]
+        pos = torch.where(ids == IMAGE_TOKEN_INDEX)[0].tolist()
+        if not pos:
+            embeds.append(F.embedding(ids, sd["model.embed_tokens.weight"]))
+            new_labels.append(lb)
+            continue
+        p0 = pos[0]
+        e = F.embedding(torch.cat([ids[:p0], ids[p0 + 1:]]), sd["model.embed_tokens.weight"])
+        embeds.append(torch.cat([e[:p0], per_sample[b].to(e.dtype), e[p0:]], 0))
+        new_labels.append(torch.cat([lb[:p0], torch.full((per_sample[b].shape[0],), IGNORE_INDEX, dtype=lb.dtype),
+                                     lb[p0 + 1:]]))
+    L = max(e.shape[0] for e in embeds)
+    H = embeds[0].shape[1]
+    out_e = torch.zeros(B, L, H, dtype=embeds[0].dtype)
+    out_l = torch.full((B, L), IGNORE_INDEX, dtype=lab.dtype)
+    out_m = torch.zeros(B, L, dtype=torch.bool)
+    out_p = torch.zeros(B, L, dtype=torch.long)
+    for b, (e, l) in enumerate(zip(embeds, new_labels)):
+        n = e.shape[0]
+        out_e[b, :n], out_l[b, :n], out_m[b, :n] = e, l, True
+        out_p[b, :n] = torch.arange(n)
+    return out_e, out_l, out_m, out_p, feats_final, masks_final, final_size, ctx_final
+
+
+def decoder_dynamic(sd, cfg, inputs_embeds, position_ids, attn_mask_2d, feats_w, aux_masks, ctx_q, final_size):
+    """CambrianLlamaModel.forward with the per-sample SVA-insertion branch, cambrian_llama.py:208-253."""
+    x = inputs_embeds
+    B = x.shape[0]
+    hd = cfg["hidden_size"] // cfg["num_attention_heads"]
+    cos, sin = rope_cos_sin(position_ids, hd, cfg["rope_theta"])
+    sites = [cfg["start_of_vision_sampler_layers"] + i * cfg["stride_of_vision_sampler_layers"]
+             for i in range(cfg["num_of_vision_sampler_layers"])]
+    s0 = cfg["image_position"]
+    for i in range(cfg["num_hidden_layers"]):
+        x = llama_layer(sd, f"model.layers.{i}.", x, cos, sin, attn_mask_2d, cfg)
+        if i in sites:
+            lqs, nls = [], []
+            for b, (h, w) in enumerate(final_size):
+                blk = x[b:b + 1, s0:s0 + h * (w + 1)].clone().view(1, h, w + 1, -1)
+                lqs.append(blk[:, :, :-1].contiguous().view(h * w, 1, -1))
+                nls.append(blk[:, :, -1:])
+            lq = sva_sampler(sd, f"model.vision_sampler_layers.{sites.index(i)}.", torch.cat(lqs, 0), ctx_q,
+                             [f.to(x.dtype) for f in feats_w], aux_masks, 1)
+            x = x.clone()
+            o = 0
+            for b, (h, w) in enumerate(final_size):
+                cur = lq[o:o + h * w].view(1, h, w, -1)
+                o += h * w
+                x[b:b + 1, s0:s0 + h * (w + 1)] = torch.cat([cur, nls[b]], 2).flatten(1, 2)
+    return rms_norm(x, sd["model.norm.weight"], cfg["rms_norm_eps"])
 
 
 # ------------------------------------------------------------------------------------------------

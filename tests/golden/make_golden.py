@@ -10,6 +10,10 @@ reference's outputs for:
                    shape (q_dim 256), kv sizes with r > 1 and letter-box style masks
   rearrange.npz    rearrange_vision_tower_features_train (cambrian_arch.py:271-287)
   collator.npz     prepare_image_info / get_padding_offset (train_fsdp.py:1039-1085) for several image sizes
+  dynamic.npz      the off-XLA (inference) branch for non-square images: unmask_attention_mask / unpad_image /
+                   rearrange_vision_tower_features_inference (cambrian_arch.py:203-330) and the whole
+                   prepare_inputs_labels_for_multimodal dynamic path (:340-451, :493-609) run on a stub model that
+                   holds reference modules (VisionTokenSampler, nn.Sequential projectors) under the reference's names
 """
 from __future__ import annotations
 
@@ -61,6 +65,97 @@ SVA_CASES = {
     "sva_connector_r4": dict(q_dim=1024, rs=[1, 1, 1, 4], layers=1, n=18, seed=12),
     "sva_inllm": dict(q_dim=256, rs=[1, 2, 1, 3], layers=1, n=32, seed=13),
 }
+
+DYN = dict(sizes=[(800, 400), (336, 336), (200, 500)], q=4, tower_dims=[96, 80], tower_sides=[4, 8], H=128, vocab=200,
+           seed=41)
+
+
+def dynamic_stub(arch, vs):
+    """A CambrianMetaForCausalLM whose get_model() holds reference modules under the reference's attribute names; the
+    'towers' are identities so the seeded tower features are the images."""
+    import torch.nn as nn
+    d = DYN
+
+    class Inner(nn.Module):
+        def __init__(self):
+            super().__init__()
+            for i, c in enumerate(d["tower_dims"]):
+                setattr(self, f"mm_projector_aux_{i}", nn.Sequential(nn.Linear(c, 1024), nn.GELU(), nn.Linear(1024, 1024),
+                                                                     nn.LayerNorm(1024)))
+            self.vision_sampler_0 = vs.VisionTokenSampler(1024, 1024, [1024, 1024], [s // d["q"] for s in d["tower_sides"]],
+                                                          1024, 2)
+            self.mm_projector = nn.Sequential(nn.Linear(1024, d["H"]), nn.GELU(), nn.Linear(d["H"], d["H"]))
+            self.embed_tokens = nn.Embedding(d["vocab"], d["H"])
+            self.vision_query = nn.Parameter(torch.zeros(1, 1024))
+            self.image_newline = nn.Parameter(torch.zeros(d["H"]))
+            self.config = type("C", (), dict(image_token_len=d["q"] ** 2, query_num_list=[d["q"] ** 2],
+                                             mm_projector_type="sva"))()
+
+        def get_vision_tower_aux_list(self):
+            return [lambda x: x for _ in d["tower_dims"]]
+
+    class Top(nn.Module, arch.CambrianMetaForCausalLM):
+        def __init__(self):
+            nn.Module.__init__(self)
+            self.model = Inner()
+            self.config = self.model.config
+            self.device = torch.device("cpu")
+
+        def get_model(self):
+            return self.model
+
+    return Top().eval()
+
+
+def dynamic_inputs():
+    d = DYN
+    rng = np.random.default_rng(d["seed"])
+    B = len(d["sizes"])
+    feats = [torch.from_numpy(rng.standard_normal((B, s * s, c)).astype(np.float32))
+             for s, c in zip(d["tower_sides"], d["tower_dims"])]
+    L = 24
+    ids = torch.from_numpy(rng.integers(3, d["vocab"], size=(B, L)))
+    for b, p0 in enumerate((5, 5, 5)):
+        ids[b, p0] = -200
+    attn = torch.ones(B, L, dtype=torch.bool)
+    attn[1, 20:] = False
+    attn[2, 15:] = False
+    labels = ids.clone()
+    return feats, ids, attn, labels
+
+
+def make_dynamic(arch, vs):
+    d = DYN
+    top = dynamic_stub(arch, vs)
+    top.load_state_dict(seeded_fill(top, d["seed"] + 1))
+    feats, ids, attn, labels = dynamic_inputs()
+    recs = {}
+    xla_flag = arch.IS_XLA_AVAILABLE
+    arch.IS_XLA_AVAILABLE = False           # the shim's torch_xla stub makes the import succeed; take the GPU/CPU branch
+    with torch.no_grad():
+        for unpad in (False, True):
+            fr, mr = top.rearrange_vision_tower_features_inference(feats, d["q"], d["sizes"], unpad=unpad)
+            for i, (f, m) in enumerate(zip(fr, mr)):
+                recs[f"re{int(unpad)}_f{i}"] = f.numpy().astype(np.float16)
+                recs[f"re{int(unpad)}_m{i}"] = m.numpy()
+        out = top.prepare_inputs_labels_for_multimodal(ids, None, attn, None, labels, feats, None, d["sizes"])
+    arch.IS_XLA_AVAILABLE = xla_flag
+    (_, pos, am, _, emb, lab, ff, mf, fs, ctx) = out
+    recs.update(emb=emb.numpy(), labels=lab.numpy(), attn=am.numpy(), final_size=np.array(fs),
+                ctx=ctx.numpy().astype(np.float16))
+    assert pos is None                                  # position_ids stay None when none were passed (:596-597)
+    for i, (f, m) in enumerate(zip(ff, mf)):
+        recs[f"final_f{i}"] = f.numpy().astype(np.float16)
+        recs[f"final_m{i}"] = m.numpy()
+    for (w, h) in [(640, 480), (480, 640), (1000, 200), (123, 457), (336, 336)]:
+        for side in (24, 27, 96):
+            recs[f"unmask_{w}x{h}_{side}"] = arch.unmask_attention_mask(torch.ones(1, side, side, dtype=torch.bool), (w, h)).numpy()
+            recs[f"unpad_{w}x{h}_{side}"] = np.array(arch.unpad_image(torch.zeros(1, side, side, 1), (w, h)).shape[1:3])
+    # parameter names / shapes in state-dict order, so the tests can regenerate the weights without the reference
+    recs["sd_keys"] = np.array(list(top.state_dict().keys()))
+    recs["sd_shapes"] = np.array([",".join(map(str, v.shape)) for v in top.state_dict().values()])
+    np.savez_compressed(os.path.join(HERE, "dynamic.npz"), **recs)
+    print("dynamic", len(recs), "final sizes", fs, "embeds", tuple(emb.shape))
 
 
 def main():
@@ -129,6 +224,7 @@ def main():
                 cm_attn=out[2].numpy(), cm_pos=out[3].numpy(), cm_aux0=out[4][0].numpy(), cm_aux1=out[4][1].numpy())
     np.savez_compressed(os.path.join(HERE, "collator.npz"), **recs)
     print("collator", len(recs))
+    make_dynamic(arch, vs)
 
 
 if __name__ == "__main__":

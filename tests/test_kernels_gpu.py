@@ -46,7 +46,7 @@ def test_layernorm_rmsnorm_fwd_bwd(capsys):
 
 
 def test_elementwise_family(capsys):
-    _run("probe2", "elem", capsys, 17)
+    _run("probe2", "elem", capsys, 23)
 
 
 def test_flash_attention_forward(capsys):

@@ -10,6 +10,8 @@ from helpers import (BF16_TOL, assert_close_bf16, ns, oracle_cfg, rel_err, sd_cp
 pytestmark = pytest.mark.gpu
 dev = "cuda"
 
+from cambrian_b200 import ops  # noqa: E402
+
 
 def _cuda_bf16(m):
     return m.to(device=dev, dtype=torch.bfloat16)
@@ -214,9 +216,8 @@ def _tiny_batch(cfg, B=2, S=96):
     return ids, labels, attn, pos, images, masks
 
 
-def _oracle_forward(model, cfg, ids, labels, attn, pos, images, masks):
+def _oracle_tower_feats(model, images):
     from oracle import cambrian_oracle as O
-    sd = sd_cpu32(model)
     towers = model.get_model().vision_tower_aux_list
     bf = lambda t: t.bfloat16().float()
     feats = []
@@ -235,6 +236,13 @@ def _oracle_forward(model, cfg, ids, labels, attn, pos, images, masks):
             else:
                 f = O.convnext_trunk(tsd, dict(depths=c["depths"], interp=t._interp_size, multi_stage=True), bf(img))
             feats.append(bf(f))  # the CUDA towers hand bf16 features to the trainable part
+    return feats
+
+
+def _oracle_forward(model, cfg, ids, labels, attn, pos, images, masks):
+    from oracle import cambrian_oracle as O
+    sd = sd_cpu32(model)
+    feats = _oracle_tower_feats(model, images)
     ocfg = oracle_cfg(cfg)
     sdg = {k: v.clone().requires_grad_() for k, v in sd.items()}
     img, feats_w, ctx_q = O.connector(sdg, ocfg, feats, masks)
@@ -358,3 +366,69 @@ def test_engine_step_and_greedy_generate():
     # bf16 vs fp32 argmax can legitimately differ on near-ties; require the first token and >= 3 of 4 to agree
     got = new[0].tolist()
     assert got[0] == toks[0] and sum(int(a == b) for a, b in zip(got, toks)) >= 3, (got, toks)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dynamic-shape branch (non-square images, per-sample unpadded query grids) — SURVEY.md §8f rank 3
+# ---------------------------------------------------------------------------------------------------------------
+def _dynamic_batch(cfg, B=2, L=40):
+    g = torch.Generator().manual_seed(17)
+    ids = torch.randint(3, cfg.vocab_size, (B, L), generator=g)
+    ids[:, cfg.image_position] = -200                      # bare <image> indicator: the branch expands it per sample
+    attn = torch.ones(B, L, dtype=torch.bool)
+    if B > 1:
+        attn[1, L - 7:] = False
+    images = [torch.randn(B, 3, r, r, generator=g) for r in tower_image_sizes(cfg)]
+    return ids, attn, images
+
+
+def test_dynamic_branch_logits_match_oracle():
+    from oracle import cambrian_oracle as O
+    cfg = tiny_cambrian_config()
+    model = _build_tiny_model(cfg).eval()
+    ids, attn, images = _dynamic_batch(cfg)
+    sizes = [(800, 400), (200, 500)]                       # 4x4 query grid -> (2, 4) and (4, 2) after unpadding
+    with torch.no_grad():
+        out = model(input_ids=ids.to(dev), attention_mask=attn.to(dev), images=[i.to(dev).bfloat16() for i in images],
+                    image_sizes=sizes)
+        sd = sd_cpu32(model)
+        ocfg = oracle_cfg(cfg)
+        feats = _oracle_tower_feats(model, images)
+        emb, _, am, pos, ff, mf, fs, ctx = O.prepare_dynamic(sd, ocfg, feats, ids, attn, None, sizes)
+        assert fs == [(2, 4), (4, 2)]
+        hid = O.decoder_dynamic(sd, ocfg, emb, pos, am, ff, mf, ctx, fs)
+        ref_logits, _ = O.lm_loss(sd, hid, None)
+    assert out.logits.shape == ref_logits.shape
+    valid = am[:, :, None].expand_as(ref_logits)
+    assert_close_bf16(out.logits.cpu()[valid], ref_logits[valid], "dynamic-branch logits", tol=5e-2, cos=0.995)
+
+
+def test_dynamic_branch_equals_static_branch_for_square_images():
+    cfg = tiny_cambrian_config()
+    model = _build_tiny_model(cfg).eval()
+    ids, attn, images = _dynamic_batch(cfg)
+    imgs = [i.to(dev).bfloat16() for i in images]
+    B = ids.shape[0]
+    with torch.no_grad():
+        static = model(input_ids=ids.to(dev), attention_mask=attn.to(dev), images=imgs, image_sizes=[(336, 336)] * B)
+        args = model._prepare_dynamic(ids.to(dev), None, attn.to(dev), None, None, imgs, [(336, 336)] * B)
+        (_, pos, am, _, emb, _, ff, mf, fs, ctx) = args
+        dyn = model.model(inputs_embeds=emb, attention_mask=am, position_ids=pos, vision_tower_aux_feature_list=ff,
+                          vision_tower_aux_attention_masks_list=mf, final_vision_feature_size=fs,
+                          global_context_feature=ctx)
+        dyn_logits = ops.gemm(dyn.last_hidden_state.reshape(-1, cfg.hidden_size).contiguous(), model.lm_head.weight,
+                              out_dtype=torch.float32).view(B, -1, cfg.vocab_size)
+    # same arithmetic, different gather path (materialised windows vs in-kernel index arithmetic): bf16-rounding level
+    assert static.logits.shape == dyn_logits.shape
+    L = dyn_logits.shape[1]
+    m = am[:, :L].bool()
+    assert rel_err(static.logits[:, :L][m], dyn_logits[:, :L][m]) < 2e-2
+
+
+def test_dynamic_branch_greedy_generate_runs():
+    cfg = tiny_cambrian_config()
+    model = _build_tiny_model(cfg).eval()
+    ids, attn, images = _dynamic_batch(cfg, B=1, L=20)
+    toks = model.generate(ids.to(dev), images=[i.to(dev).bfloat16() for i in images], image_sizes=[(200, 500)],
+                          max_new_tokens=4)
+    assert toks.shape == (1, 4) and int(toks.min()) >= 0 and int(toks.max()) < cfg.vocab_size

@@ -155,3 +155,56 @@ def test_oracle_projectors_against_reference():
     with torch.no_grad():
         torch.testing.assert_close(O.mlp2x_gelu({"p." + k: v for k, v in proj.state_dict().items()}, "p.", x), proj(x),
                                    rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# dynamic-shape (off-XLA / inference) branch for non-square images — golden generated from the reference's own
+# unmask_attention_mask / unpad_image / rearrange_vision_tower_features_inference / prepare_inputs_labels_for_multimodal
+# ---------------------------------------------------------------------------------------------------------------
+def dynamic_golden():
+    from make_golden import DYN, dynamic_inputs
+    z = np.load(os.path.join(GOLD, "dynamic.npz"))
+    shapes = {k: torch.empty([int(d) for d in sh.split(",")] if sh else [])
+              for k, sh in zip(z["sd_keys"].tolist(), z["sd_shapes"].tolist())}
+    sd = seeded_fill(shapes, DYN["seed"] + 1)
+    return z, sd, DYN, dynamic_inputs()
+
+
+def test_unmask_and_unpad_match_reference_golden():
+    z = np.load(os.path.join(GOLD, "dynamic.npz"))
+    n = 0
+    for k in z.files:
+        if k.startswith("unmask_"):
+            wh, side = k[len("unmask_"):].rsplit("_", 1)
+            w, h = map(int, wh.split("x"))
+            got = O.unmask_attention_mask(torch.ones(1, int(side), int(side), dtype=torch.bool), (w, h))
+            assert np.array_equal(got.numpy(), z[k]), k
+            shp = O.unpad_image(torch.zeros(1, int(side), int(side), 1), (w, h)).shape[1:3]
+            assert tuple(shp) == tuple(z["unpad_" + k[len("unmask_"):]]), k
+            n += 1
+    assert n == 15
+
+
+@pytest.mark.parametrize("unpad", [False, True])
+def test_rearrange_inference_matches_reference_golden(unpad):
+    z, _, d, (feats, _, _, _) = dynamic_golden()
+    fr, mr = O.rearrange_inference(feats, d["q"], d["sizes"], unpad=unpad)
+    for i, (f, m) in enumerate(zip(fr, mr)):
+        assert np.array_equal(f.numpy().astype(np.float16), z[f"re{int(unpad)}_f{i}"])       # pure gather: exact
+        assert np.array_equal(m.numpy(), z[f"re{int(unpad)}_m{i}"])
+
+
+def test_prepare_dynamic_matches_reference_golden():
+    z, sd, d, (feats, ids, attn, labels) = dynamic_golden()
+    cfg = dict(image_token_len=d["q"] ** 2, connector_depth=2)
+    with torch.no_grad():
+        emb, lab, am, pos, ff, mf, fs, ctx = O.prepare_dynamic(sd, cfg, feats, ids, attn, labels, d["sizes"])
+    assert [tuple(x) for x in z["final_size"].tolist()] == [tuple(x) for x in fs]
+    torch.testing.assert_close(emb, torch.from_numpy(z["emb"]), rtol=1e-4, atol=2e-5)
+    assert np.array_equal(lab.numpy(), z["labels"]) and np.array_equal(am.numpy(), z["attn"])
+    assert (ctx.numpy().astype(np.float32) - z["ctx"].astype(np.float32)).__abs__().max() < 2e-3     # stored as fp16
+    for i, (f, m) in enumerate(zip(ff, mf)):
+        assert np.abs(f.numpy() - z[f"final_f{i}"].astype(np.float32)).max() < 4e-3               # stored as fp16
+        assert np.array_equal(m.numpy(), z[f"final_m{i}"])
+    # right-padded position ids of the branch (cambrian_arch.py:582-584) restart at 0 for every sample
+    assert pos[0, :5].tolist() == [0, 1, 2, 3, 4]

@@ -257,6 +257,32 @@ def group_elem():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
     print(f"perf dwconv7 4x64x64x1536: {ms * 1e3:.1f} us  {2 * x.numel() * 2 / ms / 1e6:.0f} GB/s  {x.numel() * 49 * 2 / ms / 1e9:.2f} TFLOP/s fp32", flush=True)
+    # dynamic-shape helpers: window gather (+ crop), rectangular span gather / scatter, ragged embed splice
+    f = torch.randn(2, 144, 64, device=dev).bfloat16()                 # 12 x 12 grid, q = 4 -> r = 3
+    ref = f.view(2, 4, 3, 4, 3, 64).permute(0, 1, 3, 2, 4, 5).contiguous()
+    e1 = (ops.window_gather(f, 4).float() - ref.flatten(0, 2).flatten(1, 2).float()).abs().max().item()
+    e2 = (ops.window_gather(f[1:2].contiguous(), 4, (1, 3, 0, 4)).float()
+          - ref[1:2, 1:3].flatten(0, 2).flatten(1, 2).float()).abs().max().item()
+    print(f"window_gather full={e1:.1e} crop={e2:.1e} {'OK' if max(e1, e2) == 0 else 'FAIL'}", flush=True)
+    hid = torch.randn(2, 50, 64, device=dev).bfloat16()
+    lat = ops.span_gather_hw(hid, 5, 3, 4)                             # 3 rows of (4 queries + newline)
+    blk = hid[:, 5:5 + 15].view(2, 3, 5, 64)
+    e1 = (lat.float() - blk[:, :, :4].reshape(-1, 64).float()).abs().max().item()
+    h2 = hid.clone()
+    new = torch.randn_like(lat)
+    ops.span_scatter_hw_(h2, new, 5, 3, 4)
+    want = hid.clone()
+    want[:, 5:20] = torch.cat([new.view(2, 3, 4, 64), blk[:, :, 4:]], 2).flatten(1, 2)
+    e2 = (h2.float() - want.float()).abs().max().item()
+    print(f"span_hw gather={e1:.1e} scatter={e2:.1e} {'OK' if max(e1, e2) == 0 else 'FAIL'}", flush=True)
+    emb = torch.randn(100, 64, device=dev).bfloat16()
+    img = torch.randn(10, 64, device=dev).bfloat16()
+    nl = torch.randn(64, device=dev).bfloat16()
+    src = torch.tensor([3, 99, -2, -11, -(2 ** 31), -1, 0, -5], dtype=torch.int32, device=dev)
+    got = ops.embed_splice_ragged(emb, img, nl, src, 2, 4).view(8, 64)
+    want = torch.stack([emb[3], emb[99], img[0], img[9], nl, torch.zeros_like(nl), emb[0], img[3]])
+    e1 = (got.float() - want.float()).abs().max().item()
+    print(f"embed_splice_ragged err={e1:.1e} {'OK' if e1 == 0 else 'FAIL'}", flush=True)
     # reductions
     x = torch.randn(4 * 576, 1024, device=dev).bfloat16()
     e1 = rel_err(ops.group_colsum(x, 4, 1.0 / 576), x.float().view(4, 576, 1024).mean(1))
