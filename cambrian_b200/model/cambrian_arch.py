@@ -95,6 +95,19 @@ class CambrianMetaModel:
             cfg.start_of_vision_sampler_layers = getattr(model_args, "start_of_vision_sampler_layers", 0)
             cfg.stride_of_vision_sampler_layers = getattr(model_args, "stride_of_vision_sampler_layers", 1)
         self._build_vision_modules(cfg, delay_load=False)
+        adapter = getattr(model_args, "pretrain_mm_mlp_adapter", None)
+        if adapter is not None:                                                                 # :183-200
+            from ..checkpoint import load_mm_projector
+            weights = torch.load(adapter, map_location="cpu")
+            prefix = "" if any(k.startswith("model.") for k in weights) else "model."
+
+            class _Wrap:                                   # the adapter file is keyed from the ForCausalLM root
+                def __init__(self, inner):
+                    self.inner = inner
+
+                def state_dict(self):
+                    return {"model." + k: v for k, v in self.inner.state_dict().items()}
+            load_mm_projector(_Wrap(self), {prefix + k: v for k, v in weights.items()}, strict_submodules=True)
 
 
 class WindowedFeatures(list):

@@ -20,6 +20,11 @@ import torch.nn as nn
 from transformers import AutoConfig, AutoModelForCausalLM, LlamaConfig, PreTrainedModel
 from transformers.modeling_outputs import BaseModelOutputWithPast, CausalLMOutputWithPast
 
+try:  # transformers >= 5: initialisers that honour the per-parameter `_is_hf_initialized` flag
+    from transformers import initialization as _hf_init
+except ImportError:  # pragma: no cover - older transformers
+    _hf_init = None
+
 from ... import ops
 from ...autograd import DecoderLayerFn, LinearFn, LMHeadLossFn, RMSNormFn, SpanMergeFn, SpanSplitFn
 from ..cambrian_arch import IGNORE_INDEX, CambrianMetaForCausalLM, CambrianMetaModel, WindowedFeatures
@@ -220,13 +225,27 @@ class CambrianPreTrainedModel(PreTrainedModel):
     _no_split_modules = ["CBLlamaDecoderLayer"]
 
     def _init_weights(self, module):
+        """HF LlamaPreTrainedModel._init_weights.  transformers >= 5 re-runs this over every module AFTER loading a
+        checkpoint and relies on the guarded initialisers (they skip parameters flagged `_is_hf_initialized`); writing
+        through `.data` here would overwrite freshly loaded weights."""
         std = getattr(self.config, "initializer_range", 0.02)
+
+        def normal_(p):
+            if getattr(p, "_is_hf_initialized", False):
+                return
+            if _hf_init is not None:
+                _hf_init.normal_(p, mean=0.0, std=std)
+            else:
+                with torch.no_grad():
+                    p.normal_(mean=0.0, std=std)
+
         if isinstance(module, nn.Linear):
-            module.weight.data.normal_(mean=0.0, std=std)
-            if module.bias is not None:
-                module.bias.data.zero_()
+            normal_(module.weight)
+            if module.bias is not None and not getattr(module.bias, "_is_hf_initialized", False):
+                with torch.no_grad():
+                    module.bias.zero_()
         elif isinstance(module, nn.Embedding):
-            module.weight.data.normal_(mean=0.0, std=std)
+            normal_(module.weight)
 
 
 class CBLlamaModel(CambrianPreTrainedModel):

@@ -226,3 +226,52 @@ def test_gradient_allreduce_two_ranks_gloo():
     for p in procs:
         p.join(60)
     assert res == [(0, True), (1, True)]
+
+
+# ------------------------------------------------------------------------------------------------ checkpoints (§8f rank 2)
+def test_hf_checkpoint_roundtrip_and_mm_projector_overlay(tmp_path):
+    """save_pretrained -> from_pretrained keeps every tensor (the released checkpoints use this layout); the adapter-only
+    file holds exactly the reference's key filter (train_fsdp.py:255) and overlays onto a fresh model."""
+    from cambrian_b200 import checkpoint
+    from cambrian_b200.model.language_model.cambrian_llama import CambrianLlamaForCausalLM
+    cfg = tiny_cambrian_config()
+    torch.manual_seed(0)
+    m = CambrianLlamaForCausalLM(cfg)
+    m.save_pretrained(tmp_path / "full")
+    m2 = CambrianLlamaForCausalLM.from_pretrained(tmp_path / "full")
+    a, b = m.state_dict(), m2.state_dict()
+    assert list(a) == list(b)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert m2.config.mm_vision_tower_aux_token_len_list == cfg.mm_vision_tower_aux_token_len_list
+    # adapter-only checkpoint
+    path = checkpoint.save_mm_projector(m, str(tmp_path / "adapter"))
+    sd = torch.load(path)
+    assert all(any(key in k for key in checkpoint.ADAPTER_KEYS) for k in sd)
+    assert "model.vision_query" in sd and "model.image_newline" in sd and "model.mm_projector.0.weight" in sd
+    assert not any(k.startswith("model.layers.") or k.startswith("lm_head") or "embed_tokens" in k for k in sd)
+    torch.manual_seed(1)
+    fresh = CambrianLlamaForCausalLM(cfg)
+    assert not torch.equal(fresh.state_dict()["model.vision_query"], a["model.vision_query"])
+    unexpected = checkpoint.load_mm_projector(fresh, path, strict_submodules=True)
+    assert unexpected == []
+    f = fresh.state_dict()
+    assert all(torch.equal(f[k], a[k]) for k in sd)
+    assert not torch.equal(f["model.layers.0.mlp.up_proj.weight"], a["model.layers.0.mlp.up_proj.weight"])
+    # wrapper prefixes of PEFT-era files (builder.py:84-86) and shape errors
+    checkpoint.load_mm_projector(fresh, {"base_model.model." + k: v for k, v in sd.items()})
+    with pytest.raises(RuntimeError):
+        checkpoint.load_mm_projector(fresh, {"model.image_newline": torch.zeros(3)})
+    with pytest.raises(RuntimeError):
+        checkpoint.load_mm_projector(fresh, {"model.image_newline": a["model.image_newline"]}, strict_submodules=True)
+    with pytest.raises(NotImplementedError):
+        checkpoint.load_pretrained_model("x", model_name="cambrian-lora", load_tokenizer=False)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cambrian"), reason="reference tree only exists in the build container")
+def test_state_dict_keys_equal_the_reference_modules():
+    """Connector key set == the reference's own modules' (instantiated through the shim)."""
+    from oracle import ref_shim
+    from cambrian_b200.model.vision_sampler import VisionTokenSampler
+    vs = ref_shim.ref_module("cambrian.model.vision_sampler")
+    for args in [(1024, 1024, [1024] * 4, [1, 1, 1, 1], 1024, 3), (256, 1024, [1024] * 3, [1, 2, 3], 1024, 1)]:
+        assert list(vs.VisionTokenSampler(*args).state_dict()) == list(VisionTokenSampler(*args).state_dict())
