@@ -313,9 +313,12 @@ class CambrianLlamaModel(CambrianMetaModel, CBLlamaModel):
         q_side = int(q_num ** 0.5)
         hidden = inputs_embeds.contiguous()
         all_hidden = () if output_hidden_states else None
+        z3 = getattr(self, "_zero3", None)
         for i, layer in enumerate(self.layers):
             if output_hidden_states:
                 all_hidden += (hidden,)
+            if z3 is not None:
+                z3.before_layer(i)                      # ZeRO-3 inference: weights of layer i resident, i+1 in flight
             hidden = layer.infer(hidden, rt, cache) if cache is not None else layer(hidden, rt)
             if i in sites and isinstance(vision_tower_aux_feature_list, WindowedFeatures):
                 # per-sample unpadded query grids (cambrian_llama.py:208-253), inference only: the latent queries of
@@ -492,7 +495,8 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
             if eos:
                 for e in eos:
                     done |= nxt == e
-                if bool(done.all()):
+                z3 = getattr(self.get_model(), "_zero3", None)
+                if (z3.all_done(done) if z3 is not None else bool(done.all())):
                     break
             if step + 1 == max_new:
                 break

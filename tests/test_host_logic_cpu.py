@@ -275,3 +275,50 @@ def test_state_dict_keys_equal_the_reference_modules():
     vs = ref_shim.ref_module("cambrian.model.vision_sampler")
     for args in [(1024, 1024, [1024] * 4, [1, 1, 1, 1], 1024, 3), (256, 1024, [1024] * 3, [1, 2, 3], 1024, 1)]:
         assert list(vs.VisionTokenSampler(*args).state_dict()) == list(VisionTokenSampler(*args).state_dict())
+
+
+# ------------------------------------------------------------------------------------------------ ZeRO-3 inference (§8e, config 5)
+def _zero3_worker(rank, world, port, n_layers, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from cambrian_b200.model.language_model.cambrian_llama import CambrianLlamaForCausalLM
+        from cambrian_b200.sharded import Zero3Inference
+        cfg = tiny_cambrian_config()
+        cfg.num_hidden_layers = n_layers
+        torch.manual_seed(5)
+        m = CambrianLlamaForCausalLM(cfg).to(torch.bfloat16)
+        want = [{k: v.clone() for k, v in layer.state_dict().items()} for layer in m.get_model().layers]
+        z = Zero3Inference(m)
+        assert all(p.numel() == 0 for layer in m.get_model().layers for p in layer.parameters())
+        assert z.shards[0].numel() * world >= sum(v.numel() for v in want[0].values())
+        ok = True
+        for sweep in range(3):                        # prefill + two decode steps: the prefetch wraps around
+            for i, layer in enumerate(m.get_model().layers):
+                z.before_layer(i)
+                got = layer.state_dict()
+                ok &= all(torch.equal(got[k], want[i][k]) for k in want[i])
+                qkv, gu, _, _ = layer._fused()        # fused views stay zero-copy inside the staging buffer
+                ok &= qkv.data_ptr() == layer.self_attn.q_proj.weight.data_ptr()
+        done = torch.tensor([rank == 0])
+        ok &= z.all_done(done) is False and z.all_done(torch.tensor([True])) is True
+        q.put((rank, bool(ok), z.gathers))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_layers", [4, 3])
+def test_zero3_inference_gathers_every_layer_world2(n_layers):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + n_layers
+    procs = [ctx.Process(target=_zero3_worker, args=(r, 2, port, n_layers, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert [r[1] for r in res] == [True, True], res
+    assert res[0][2] == 3 * n_layers + 1              # one gather per layer visit + the wrapped prefetch left in flight

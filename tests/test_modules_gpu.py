@@ -432,3 +432,19 @@ def test_dynamic_branch_greedy_generate_runs():
     toks = model.generate(ids.to(dev), images=[i.to(dev).bfloat16() for i in images], image_sizes=[(200, 500)],
                           max_new_tokens=4)
     assert toks.shape == (1, 4) and int(toks.min()) >= 0 and int(toks.max()) < cfg.vocab_size
+
+
+def test_zero3_sharded_generate_is_token_identical():
+    """ZeRO-3 inference sharding (config 5) at world size 1: the gather pipeline (staging slots, wrap-around prefetch,
+    parameter re-pointing) must not change a single generated token."""
+    from cambrian_b200.sharded import Zero3Inference
+    cfg = tiny_cambrian_config()
+    model = _build_tiny_model(cfg).eval()
+    ids, attn, images = _dynamic_batch(cfg, B=2, L=24)
+    imgs = [i.to(dev).bfloat16() for i in images]
+    kw = dict(images=imgs, image_sizes=[(336, 336)] * 2, attention_mask=attn.to(dev), max_new_tokens=6)
+    ref = model.generate(ids.to(dev), **kw)
+    z = Zero3Inference(model)
+    got = model.generate(ids.to(dev), **kw)
+    assert torch.equal(ref, got)
+    assert z.gathers >= 6 * cfg.num_hidden_layers
