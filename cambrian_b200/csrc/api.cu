@@ -85,6 +85,11 @@ int adamw_launch(float*, float*, float*, const void*, void*, long long, float, f
                  cudaStream_t);
 int span_gather_launch(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int span_scatter_launch(void*, const void*, int, int, int, int, int, int, cudaStream_t);
+int resample_ksize(int, int);
+void resample_coeffs(int, int, int*, int*);
+long long preprocess_workspace_bytes(int, int, int);
+int preprocess_launch(const uint8_t*, int, int, int, const int*, const float*, const float*, void*, uint8_t*, void*, long long,
+                      cudaStream_t);
 int window_gather_launch(const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
 int embed_splice_ragged_launch(void*, const void*, const void*, const void*, const int*, long long, int, cudaStream_t);
 
@@ -244,6 +249,26 @@ int cb_embed_splice_ragged(void* out, const void* embed, const void* img, const 
 }
 int cb_span_scatter(void* hidden, const void* lat, int B, int S, int H, int start, int q_side, void* stream) {
   return cb::span_scatter_launch(hidden, lat, B, S, H, start, q_side, q_side, ST(stream));
+}
+int cb_resample_ksize(int in_size, int out_size) {
+  if (in_size <= 0 || out_size <= 0) return 0;
+  return cb::resample_ksize(in_size, out_size);
+}
+int cb_resample_coeffs(int in_size, int out_size, int32_t* bounds, int32_t* kk) {
+  if (in_size <= 0 || out_size <= 0 || !bounds || !kk) return cb::set_error(CB_ERR_INVALID, "resample_coeffs: bad arguments");
+  cb::resample_coeffs(in_size, out_size, bounds, kk);
+  return CB_OK;
+}
+int64_t cb_preprocess_workspace_bytes(int H, int W, int R) {
+  if (H <= 0 || W <= 0 || R <= 0) return 0;
+  return cb::preprocess_workspace_bytes(H, W, R);
+}
+int cb_preprocess_image(const uint8_t* img, int H, int W, int R, const int32_t* pad_rgb, const float* mean,
+                        const float* std, void* out, uint8_t* out_u8, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+  if (!img || !pad_rgb || !mean || !std || !out || !workspace)
+    return cb::set_error(CB_ERR_INVALID, "preprocess_image: null argument");
+  return cb::preprocess_launch(img, H, W, R, pad_rgb, mean, std, out, out_u8, workspace, workspace_bytes, ST(stream));
 }
 int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int step, float grad_scale, void* stream) {

@@ -490,3 +490,35 @@ def embed_splice_ragged(embed_w, img, newline, src, batch: int, max_len: int):
                                              ptr(newline) if newline is not None else None, ptr(src), batch * max_len, H,
                                              stream()), "cb_embed_splice_ragged")
     return out
+
+
+def resample_coeffs(in_size: int, out_size: int):
+    """Host-side Pillow-compatible bicubic coefficient tables: (bounds int32 [out, 2], kk int32 [out, ksize])."""
+    import ctypes
+    lib = _lib.load()
+    ks = lib.cb_resample_ksize(in_size, out_size)
+    bounds = torch.empty((out_size, 2), dtype=torch.int32)
+    kk = torch.empty((out_size, ks), dtype=torch.int32)
+    check(lib.cb_resample_coeffs(in_size, out_size, bounds.data_ptr(), kk.data_ptr()), "cb_resample_coeffs")
+    return bounds, kk
+
+
+def preprocess_image(img_u8, size: int, pad_rgb, mean, std, return_u8: bool = False):
+    """img_u8: CUDA uint8 [H, W, 3] RGB -> bf16 [3, size, size] = normalise(resize(expand2square(img))) with Pillow's
+    exact uint8 bicubic arithmetic (mm_utils.py:186-201).  Optionally also returns the resized uint8 image."""
+    import ctypes
+    if not img_u8.is_cuda or img_u8.dtype != torch.uint8 or img_u8.dim() != 3 or img_u8.shape[2] != 3:
+        raise ValueError("preprocess_image: expected a CUDA uint8 [H, W, 3] tensor")
+    img_u8 = img_u8.contiguous()
+    H, W = int(img_u8.shape[0]), int(img_u8.shape[1])
+    lib = _lib.load()
+    nbytes = lib.cb_preprocess_workspace_bytes(H, W, size)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=img_u8.device)
+    out = torch.empty((3, size, size), dtype=torch.bfloat16, device=img_u8.device)
+    u8 = torch.empty((size, size, 3), dtype=torch.uint8, device=img_u8.device) if return_u8 else None
+    pad = (ctypes.c_int32 * 3)(*[int(v) for v in pad_rgb])
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    sd = (ctypes.c_float * 3)(*[float(v) for v in std])
+    check(lib.cb_preprocess_image(ptr(img_u8), H, W, size, ctypes.addressof(pad), ctypes.addressof(m), ctypes.addressof(sd),
+                                  ptr(out), ptr(u8), ptr(ws), nbytes, stream()), "cb_preprocess_image")
+    return (out, u8) if return_u8 else out

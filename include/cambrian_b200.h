@@ -179,6 +179,18 @@ int cb_window_gather(const void* feat, void* out, int B, int q_side, int r, int 
  * zeros if src == -1 (padding), newline if src == INT32_MIN, img[-2 - src] otherwise; rows = B * max_len. */
 int cb_embed_splice_ragged(void* out, const void* embed, const void* img, const void* newline, const int32_t* src,
                            int64_t rows, int H, void* stream);
+/* Image preprocessing on the GPU — replaces, per tower, the host chain of `process_images`
+ * (mm_utils.py:186-201): expand2square(img, int(mean*255)) -> PIL Image.resize((R,R)) [bicubic, antialiased, uint8,
+ * bit-exact with Pillow's Resample.c] -> x/255 -> (x-mean)/std.  img: device uint8 [H,W,3] RGB; out: bf16 [3,R,R];
+ * out_u8 (optional, may be NULL): the resized uint8 image [R,R,3]; pad_rgb / mean / std: HOST arrays of 3.
+ * cb_resample_ksize / cb_resample_coeffs are the host-side coefficient generator (bounds [out,2], kk [out,ksize],
+ * 22-bit fixed point) exposed for tests. */
+int cb_resample_ksize(int in_size, int out_size);
+int cb_resample_coeffs(int in_size, int out_size, int32_t* bounds, int32_t* kk);
+int64_t cb_preprocess_workspace_bytes(int H, int W, int R);
+int cb_preprocess_image(const uint8_t* img, int H, int W, int R, const int32_t* pad_rgb, const float* mean,
+                        const float* std, void* out, uint8_t* out_u8, void* workspace, int64_t workspace_bytes,
+                        void* stream);
 /* AdamW on fp32 master weights / moments with bf16 gradients, writing the bf16 compute copy */
 int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int step, float grad_scale, void* stream);

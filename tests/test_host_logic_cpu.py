@@ -322,3 +322,48 @@ def test_zero3_inference_gathers_every_layer_world2(n_layers):
         p.join(timeout=60)
     assert [r[1] for r in res] == [True, True], res
     assert res[0][2] == 3 * n_layers + 1              # one gather per layer visit + the wrapped prefetch left in flight
+
+
+# ------------------------------------------------------------------------------------------------ preprocessing (§8f rank 4)
+def _pil_equivalent_resize(arr, R, pad):
+    """numpy emulation of the two CUDA passes using the library's coefficient tables (host entry point)."""
+    from cambrian_b200 import ops
+    H, W, _ = arr.shape
+    S = max(H, W)
+    sq = np.empty((S, S, 3), dtype=np.int64)
+    sq[...] = np.array(pad)
+    oy, ox = ((W - H) // 2, 0) if W > H else (0, (H - W) // 2)
+    sq[oy:oy + H, ox:ox + W] = arr
+    bounds, kk = ops.resample_coeffs(S, R)
+    bounds, kk = bounds.numpy(), kk.numpy().astype(np.int64)
+
+    def one_pass(src):                                   # resample axis 1
+        out = np.empty((src.shape[0], R, 3), dtype=np.int64)
+        for xx in range(R):
+            x0, n = bounds[xx]
+            acc = (src[:, x0:x0 + n, :] * kk[xx, :n, None]).sum(1) + (1 << 21)
+            out[:, xx, :] = np.clip(acc >> 22, 0, 255)
+        return out
+    tmp = one_pass(sq)
+    return one_pass(tmp.transpose(1, 0, 2)).transpose(1, 0, 2).astype(np.uint8)
+
+
+@pytest.mark.parametrize("hw,R", [((480, 640), 336), ((700, 300), 384), ((100, 130), 336), ((336, 336), 336),
+                                  ((1500, 1100), 1024)])
+def test_resample_coefficients_reproduce_pillow_bit_exact(hw, R):
+    """Pins the restated Resample.c arithmetic (third-party: Pillow, the `Image.resize` of mm_utils.py:194) against the
+    installed Pillow on the reference's own call chain expand2square -> resize."""
+    from PIL import Image
+    rng = np.random.default_rng(hw[0] * 7 + R)
+    arr = rng.integers(0, 256, size=(hw[0], hw[1], 3), dtype=np.uint8)
+    pad = (122, 116, 104)
+    img = Image.fromarray(arr)
+    w, h = img.size
+    if w != h:                                            # expand2square, mm_utils.py:153-164
+        s = max(w, h)
+        sq = Image.new(img.mode, (s, s), pad)
+        sq.paste(img, (0, (w - h) // 2) if w > h else ((h - w) // 2, 0))
+        img = sq
+    want = np.asarray(img.resize((R, R)))
+    got = _pil_equivalent_resize(arr, R, pad)
+    assert np.array_equal(got, want)

@@ -88,3 +88,45 @@ def test_full_size_properties():
     vv = qkv[..., (nh + nkv) * hd:].view(1, S, nkv, hd)
     o = ops.attn_fwd(qv, kv, vv, causal=True)
     assert torch.equal(o[0, 0], vv[0, 0].repeat_interleave(nh // nkv, 0))
+
+
+@pytest.mark.parametrize("hw,R", [((480, 640), 336), ((700, 300), 384), ((90, 130), 336), ((336, 336), 336),
+                                  ((1500, 1100), 1024)])
+def test_gpu_preprocess_matches_pillow_bit_exact(hw, R):
+    """cb_preprocess_image vs the reference's host chain (mm_utils.py:186-201): expand2square -> PIL resize (bicubic,
+    uint8) is reproduced bit for bit; the normalised bf16 tensor matches (x/255 - mean)/std to bf16 rounding."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from cambrian_b200 import ops
+    rng = np.random.default_rng(hw[0] + R)
+    arr = rng.integers(0, 256, size=(hw[0], hw[1], 3), dtype=np.uint8)
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    pad = tuple(int(x * 255) for x in mean)
+    img = Image.fromarray(arr)
+    w, h = img.size
+    if w != h:
+        s = max(w, h)
+        sq = Image.new(img.mode, (s, s), pad)
+        sq.paste(img, (0, (w - h) // 2) if w > h else ((h - w) // 2, 0))
+        img = sq
+    want_u8 = np.asarray(img.resize((R, R)))
+    out, u8 = ops.preprocess_image(torch.from_numpy(arr).cuda(), R, pad, mean, std, return_u8=True)
+    assert np.array_equal(u8.cpu().numpy(), want_u8)
+    want = (torch.from_numpy(want_u8).permute(2, 0, 1).float() / 255.0 - torch.tensor(mean).view(3, 1, 1)) / \
+        torch.tensor(std).view(3, 1, 1)
+    assert (out.float().cpu() - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()
+
+
+def test_process_images_returns_one_tensor_per_tower():
+    import numpy as np
+    import torch
+    from cambrian_b200.model.multimodal_encoder.towers import SimpleImageProcessor
+    from cambrian_b200.preprocess import process_images
+    procs = [SimpleImageProcessor(384, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
+             SimpleImageProcessor(336, (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))]
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, size=(200, 320, 3), dtype=np.uint8), rng.integers(0, 256, size=(500, 400, 3), dtype=np.uint8)]
+    outs = process_images(imgs, procs)
+    assert [tuple(o.shape) for o in outs] == [(2, 3, 384, 384), (2, 3, 336, 336)]
+    assert all(o.dtype == torch.bfloat16 and o.is_cuda and torch.isfinite(o.float()).all() for o in outs)
