@@ -85,10 +85,13 @@ def make_host_batch(cfg, B, S, seed, res):
     pos = torch.arange(S)[None].expand(B, S).contiguous()
     images = [torch.randn(B, 3, r, r, generator=g).bfloat16() for r in res]
     n_valid = int((labels[:, 1:] != -100).sum())
+    from cambrian_b200.train.collator import valid_label_ranges
+    ranges, nv2 = valid_label_ranges(labels)        # host-side collator hint: rows that can carry a loss term
+    assert nv2 == n_valid
     batch = dict(input_ids=ids, labels=labels, attention_mask=attn, position_ids=pos, images=images)
     for k, v in batch.items():
         batch[k] = [t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory()
-    return batch, n_valid
+    return batch, (n_valid, ranges)
 
 
 def to_device(batch, dev):
@@ -365,22 +368,22 @@ def main():
     B, S = args.micro_batch, args.seq
     host_batches = [make_host_batch(cfg, B, S, 1000 * rank + i, res) for i in range(2)]
     dev_batch, h2d_bytes = to_device(host_batches[0][0], dev)
-    n_valid = host_batches[0][1]
+    n_valid, label_ranges = host_batches[0][1]
     img_pos = [cfg.image_position] * B  # known to the collator (train_fsdp.py:1089-1165); avoids a D2H scan per step
     torch.cuda.synchronize()
 
     def step_resident():
         engine.zero_grad()
-        out = model(**dev_batch, num_valid_labels=n_valid, image_positions=img_pos)
+        out = model(**dev_batch, num_valid_labels=n_valid, image_positions=img_pos, label_ranges=label_ranges)
         out.loss.backward()
         engine.step()
         return out.loss
 
     def step_e2e(i):
-        hb, nv = host_batches[i % 2]
+        hb, (nv, lr) = host_batches[i % 2]
         db, _ = to_device(hb, dev)
         engine.zero_grad()
-        out = model(**db, num_valid_labels=nv, image_positions=img_pos)
+        out = model(**db, num_valid_labels=nv, image_positions=img_pos, label_ranges=lr)
         out.loss.backward()
         engine.step()
         return float(out.loss.item())  # device -> host read of the step's result
@@ -487,7 +490,11 @@ def main():
         if "sva_fwd" in agg:
             by, tms, n = agg["sva_fwd"]
             roof_sva["in_step_achieved"] = by / (tms / 1000.0) / 1e9  # B=4 inputs (38 MB) are L2-resident in the step
-    model_tf = value * STEP_TF if not args.small else None
+    # executed FLOPs per sample: the fused loss skips the vocabulary GEMMs (3 x 2*H*V per row) of rows whose shifted
+    # label is ignore_index — identical loss / gradients, fewer FLOPs than BASELINE.md's 104.3 TFLOP accounting
+    rows_done = sum(b - a for a, b in label_ranges)
+    skipped_tf = 3 * 2.0 * cfg.hidden_size * cfg.vocab_size * (B * S - rows_done) / B / 1e12
+    model_tf = value * (STEP_TF - skipped_tf) if not args.small else None
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic", per_gpu=value / world,
@@ -497,7 +504,9 @@ def main():
                         "micro_batch_per_gpu": B, "global_batch": B * world, "seq_len": S,
                         "parallelism": f"dp{world}", "activation_recompute": bool(args.recompute),
                         "optimizer": "AdamW fp32 master + bf16 grads, fused", "trainable_params": n_train,
-                        "frozen_tower_params": n_tower, "l2_policy": "inputs larger than L2 (16 GB weights streamed per pass)"},
+                        "frozen_tower_params": n_tower,
+                        "lm_head_rows": f"{rows_done} of {B * S} (rows with an ignored label skip the vocabulary GEMMs; "
+                                        f"loss and gradients identical; MFU counts executed FLOPs only)", "l2_policy": "inputs larger than L2 (16 GB weights streamed per pass)"},
                 gpu_launches=int(launches), host_enqueue_ms_per_step=round(host_enqueue_ms, 1), loss=float(loss),
                 peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=4),

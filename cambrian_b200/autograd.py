@@ -446,11 +446,30 @@ class LMHeadLossFn(torch.autograd.Function):
         V = weight.shape[0]
         dev = hidden.device
         chunk = meta.get("chunk", 4096)
-        loss_rows = torch.empty(rows, dtype=torch.float32, device=dev)
-        acc = torch.zeros(2, dtype=torch.float32, device=dev)
         n_valid = meta["n_valid"]  # python int (known on the host from the collator) — no device sync
         train = meta["train"]
         p_w = meta["params"][0]
+        # Rows whose shifted label is ignore_index contribute neither loss nor gradient.  When the collator hands over
+        # the row ranges that can hold a valid label (host ints, `label_ranges`), only those rows are pushed through the
+        # vocabulary GEMMs: they are packed into one dense buffer (device-to-device copies), dhidden of all other rows
+        # is exactly zero.  Without the hint every row is processed, as the reference does.
+        ranges = meta.get("label_ranges")
+        dh_full = None
+        if ranges is not None:
+            ranges = [(int(a), int(b)) for a, b in ranges if b > a]
+            n_rows = sum(b - a for a, b in ranges)
+            hc = torch.empty((max(n_rows, 1), H), dtype=h2.dtype, device=dev)
+            lc = torch.full((max(n_rows, 1),), -100, dtype=labels.dtype, device=dev)
+            o = 0
+            for a, b in ranges:
+                hc[o:o + b - a].copy_(h2[a:b])
+                lc[o:o + b - a].copy_(labels[a:b])
+                o += b - a
+            if train:
+                dh_full = torch.zeros_like(h2)
+            h2, labels, rows = hc, lc, max(n_rows, 1)
+        loss_rows = torch.empty(rows, dtype=torch.float32, device=dev)
+        acc = torch.zeros(2, dtype=torch.float32, device=dev)
         dh = torch.empty_like(h2) if train else None
         gscale = 1.0 / max(n_valid, 1)
         logits = torch.empty((min(chunk, rows), V), dtype=torch.bfloat16, device=dev)
@@ -468,6 +487,12 @@ class LMHeadLossFn(torch.autograd.Function):
                     wgrad(p_w, lg, h2[r0:r1])
                 else:
                     ops.gemm(lg, h2[r0:r1], a_mn=True, b_mn=True, out=dw_local, accumulate=r0 > 0)
+        if dh_full is not None:
+            o = 0
+            for a, b in ranges:
+                dh_full[a:b].copy_(dh[o:o + b - a])
+                o += b - a
+            dh = dh_full
         ctx.train = train
         ctx.hshape = hidden.shape
         ctx.has_dw = dw_local is not None

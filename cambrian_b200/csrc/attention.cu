@@ -17,7 +17,8 @@
 // Backward (one CTA = 128 keys of one KV head; loops over the query heads of the GQA group and the query tiles):
 //   S^T = K Q^T and dP^T = V dO^T in TMEM; threads (one per key row) form P^T (bf16, back into TMEM as the A
 //   operand of dV += P^T dO) and dS^T (bf16, smem: K-major A of dK += dS^T Q and MN-major A of dQ_i = dS K);
-//   dK / dV accumulate in TMEM over the whole loop, dQ partials are reduced with fp32 vector atomics.
+//   dK / dV accumulate in TMEM over the whole loop, dQ partials are staged as fp32 tiles in the Q / dO stage the
+//   iteration just retired and reduce-added into global memory by TMA (cp.reduce.async.bulk.tensor .add).
 #include "common.cuh"
 #include <cudaTypedefs.h>
 
@@ -366,7 +367,8 @@ struct BwdCfg {
 template <int HDP>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const __grid_constant__ CUtensorMap tmdQ, AttnBwdParams p) {
   using Cfg = BwdCfg<HDP>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -384,7 +386,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t pds_full = bars + 8u * 6;   // P^T (TMEM) and dS^T (smem) written by the 128 threads
   const uint32_t dq_full = bars + 8u * 7;    // dQ partial ready in TMEM (also: dV/dK MMAs of this iteration retired)
   const uint32_t dq_done = bars + 8u * 8;    // dQ partial read out by the 128 threads
-  const uint32_t tmem_slot = bars + 8u * 9;
+  const uint32_t dq_staged = bars + 8u * 9;  // fp32 dQ partial staged in this iteration's (retired) Q / dO stage
+  const uint32_t tmem_slot = bars + 8u * 10;
   float* stat = reinterpret_cast<float*>(smem_raw + (sStat - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -407,6 +410,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmdO);
+    tma_prefetch_desc(&tmdQ);
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(qd_full(s), 1);
@@ -416,6 +420,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(pds_full, 256);
     mbar_init(dq_full, 1);
     mbar_init(dq_done, 256);
+    mbar_init(dq_staged, 256);
     mbar_fence_init();
   }
   if (warp == 5) tmem_alloc(tmem_slot, 512);
@@ -437,20 +442,39 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_4d(sK + a * 16384, &tmK, kv_full, a * 64, g, k0, b);
         tma_load_4d(sV + a * 16384, &tmV, kv_full, a * 64, g, k0, b);
       }
-      int st = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < n_iter; ++it) {
+      auto load_qd = [&](int it) {
+        const int st = it & 1;
         const int h = g * G + it / n_i;
         const int qi0 = (i_begin + it % n_i) * 128;
-        mbar_wait(qd_empty(st), ph ^ 1u);
         mbar_arrive_expect_tx(qd_full(st), 2 * Cfg::TILE);
 #pragma unroll
         for (int a = 0; a < Cfg::ATOMS; ++a) {
           tma_load_4d(sQ + st * Cfg::TILE + a * 16384, &tmQ, qd_full(st), a * 64, h, qi0, b);
           tma_load_4d(sdO + st * Cfg::TILE + a * 16384, &tmdO, qd_full(st), a * 64, h, qi0, b);
         }
-        if (++st == 2) { st = 0; ph ^= 1u; }
+      };
+      if (n_iter > 0) load_qd(0);
+      if (n_iter > 1) load_qd(1);
+      for (int it = 0; it < n_iter; ++it) {
+        // The compute warps stage the fp32 dQ partial of iteration `it` in the Q / dO stage that iteration just retired
+        // (its MMAs completed before dq_full).  This thread reduce-adds it into global memory with TMA — per-thread
+        // `red.global` on 32 different rows per instruction cost 32 % of the kernel — waits until the engine has READ the
+        // tile, and only then refills the stage with the operands of iteration it + 2 (still a full iteration ahead).
+        const int st = it & 1;
+        const int h = g * G + it / n_i;
+        const int qi0 = (i_begin + it % n_i) * 128;
+        mbar_wait(dq_staged, it & 1);
+#pragma unroll
+        for (int c = 0; c < Cfg::OCH; ++c) {
+          const uint32_t src = (c * 16384 < Cfg::TILE) ? sQ + st * Cfg::TILE + c * 16384
+                                                       : sdO + st * Cfg::TILE + (c * 16384 - Cfg::TILE);
+          tma_reduce_add_4d(&tmdQ, src, c * 32, h, qi0, b);
+        }
+        bulk_commit_group();
+        bulk_wait_group_read0();
+        if (it + 2 < n_iter) load_qd(it + 2);
       }
+      bulk_wait_group0();
     }
   } else if (warp == 5) {
     if (lane == 0) {
@@ -587,27 +611,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
       {
-        // pull the whole dQ row out of TMEM first and release region B immediately: the next iteration's S^T / dP^T MMAs
-        // then overlap with the (slow) global reductions below
-        const int qi = qi0 + row;
-        float* dqp = p.dq_acc + (((long long)b * p.Sq + qi) * p.nh + h) * p.hd;
+        // dQ partial: TMEM -> registers -> fp32 tile in this iteration's retired Q / dO stage (128B-swizzled boxes of
+        // [128 rows][32 floats], matching the reduce tensor map); the producer thread issues the TMA reduce-add
         constexpr int HC = Cfg::OCH / 2;  // 32-column chunks of the dQ row owned by this warp
         uint32_t r[HC * 32];
 #pragma unroll
         for (int c = 0; c < HC; ++c) tmem_ld32(tB + lane_off + (ch * HC + c) * 32, r + c * 32);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(dq_done);
-        if (qi < p.Sq) {
+        mbar_arrive(dq_done);  // region B is free: the next iteration's S^T / dP^T MMAs overlap with the readout below
+        const int st = it & 1;
 #pragma unroll
-          for (int u = 0; u < HC * 8; ++u) {
-            const int d0 = ch * HC * 32 + u * 4;
-            if (d0 < p.hd)
-              atomicAdd(reinterpret_cast<float4*>(dqp + d0),
-                        make_float4(__uint_as_float(r[u * 4]), __uint_as_float(r[u * 4 + 1]),
-                                    __uint_as_float(r[u * 4 + 2]), __uint_as_float(r[u * 4 + 3])));
+        for (int rd = 0; rd < HC; ++rd) {
+          const int c = ch * HC + rd;
+          const uint32_t box = (c * 16384 < Cfg::TILE) ? sQ + st * Cfg::TILE + c * 16384
+                                                       : sdO + st * Cfg::TILE + (c * 16384 - Cfg::TILE);
+          const uint32_t dst = box + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + ((j ^ (row & 7)) << 4)),
+                         "r"(r[rd * 32 + j * 4]), "r"(r[rd * 32 + j * 4 + 1]), "r"(r[rd * 32 + j * 4 + 2]),
+                         "r"(r[rd * 32 + j * 4 + 3])
+                         : "memory");
           }
         }
+        fence_proxy_async_smem();
+        mbar_arrive(dq_staged);
       }
     }
     // ---- epilogue: dK (x softmax scale), dV -> bf16
@@ -739,7 +768,7 @@ int attn_fwd_launch(const void* q, const void* k, const void* v, void* o, float*
 
 template <int HDP>
 static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
-                      const AttnBwdParams& p, cudaStream_t st) {
+                      const CUtensorMap& tdq, const AttnBwdParams& p, cudaStream_t st) {
   using Cfg = BwdCfg<HDP>;
   auto kern = attn_bwd_kernel<HDP>;
   static bool attr = false;
@@ -749,7 +778,7 @@ static int launch_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     attr = true;
   }
   dim3 grid((p.Skv + 127) / 128, p.nkv, p.B);
-  kern<<<grid, 320, Cfg::SMEM, st>>>(tq, tk, tv, tdo, p);
+  kern<<<grid, 320, Cfg::SMEM, st>>>(tq, tk, tv, tdo, tdq, p);
   CB_CUDA_LAUNCH_CHECK("attn_bwd");
   return CB_OK;
 }
@@ -782,8 +811,26 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const void* o, 
   p.lse = lse; p.delta = delta; p.kmask = (const uint8_t*)kmask;
   p.B = B; p.nh = nh; p.nkv = nkv; p.Sq = Sq; p.Skv = Skv; p.hd = hd; p.causal = causal;
   p.scale_log2 = scale * LOG2E; p.scale = scale;
-  if (hd == 64) return launch_bwd<64>(tq, tk, tv, tdo, p, st);
-  return launch_bwd<128>(tq, tk, tv, tdo, p, st);
+  CUtensorMap tdq;  // fp32 dQ accumulator [B, Sq, nh, hd]: reduce-add target, box = 32 floats x 128 query rows
+  {
+    auto fn = encode_fn();
+    if (!fn) return set_error(CB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    CB_CHECK_ARG((reinterpret_cast<uintptr_t>(dq_acc) & 15u) == 0, "attention bwd: dq_acc must be 16-byte aligned");
+    cuuint64_t dims[4] = {(cuuint64_t)hd, (cuuint64_t)nh, (cuuint64_t)Sq, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)hd * 4, (cuuint64_t)nh * hd * 4, (cuuint64_t)Sq * nh * hd * 4};
+    cuuint32_t box[4] = {32, 1, 128, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = CUDA_SUCCESS;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      r = fn(&tdq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_acc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+      cudaFree(0);
+    }
+    if (r != CUDA_SUCCESS) return set_error(CB_ERR_CUDA, "cuTensorMapEncodeTiled(dq) failed (%d)", (int)r);
+  }
+  if (hd == 64) return launch_bwd<64>(tq, tk, tv, tdo, tdq, p, st);
+  return launch_bwd<128>(tq, tk, tv, tdo, tdq, p, st);
 }
 
 }  // namespace cb

@@ -403,10 +403,12 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
                 image_aux_attention_masks_list: Optional[List[torch.Tensor]] = None,
                 image_sizes: Optional[List[List[int]]] = None, return_dict: Optional[bool] = None,
                 cache_position=None, num_valid_labels: Optional[int] = None,
-                image_positions: Optional[List[int]] = None, **kw):
+                image_positions: Optional[List[int]] = None, label_ranges=None, **kw):
         """cambrian_llama.py:297-434.  Extensions (host-side hints the collator already has; both avoid a device->host
         sync per step): `num_valid_labels` = number of non-ignored shifted labels, `image_positions` = index of the
-        <image> indicator per sample of an already-expanded batch."""
+        <image> indicator per sample of an already-expanded batch; `label_ranges` = host list of (row_start, row_end) over
+        the flattened [B*S] positions outside of which every SHIFTED label is ignore_index (train/collator.py:
+        valid_label_ranges) — the fused loss then skips the vocabulary GEMMs of rows that cannot contribute."""
         feats = masks = final_size = ctx_feat = None
         if inputs_embeds is None:
             (input_ids, position_ids, attention_mask, past_key_values, inputs_embeds, labels, feats, masks, final_size,
@@ -431,7 +433,8 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
                 num_valid_labels = int(((shift != IGNORE_INDEX) & (shift >= 0) & (shift < self.vocab_size)).sum())
         if labels is not None and fused:
             meta = dict(shift_labels=shift, n_valid=num_valid_labels, train=torch.is_grad_enabled(),
-                        params=(self.lm_head.weight,), chunk=getattr(self.config, "lm_loss_chunk", 4096))
+                        params=(self.lm_head.weight,), chunk=getattr(self.config, "lm_loss_chunk", 4096),
+                        label_ranges=label_ranges)
             loss = LMHeadLossFn.apply(meta, hidden, self.lm_head.weight)
         else:
             logits_bf16 = LinearFn.apply(hidden, self.lm_head.weight, None)                     # :408

@@ -83,3 +83,18 @@ def prepare_multimodal_data(input_ids, labels, attention_mask, image_sizes, imag
         out_pos.append(pos[:max_length])
     return (torch.stack(out_ids), torch.stack(out_labels), torch.stack(out_mask), torch.stack(out_pos),
             [torch.stack(m) for m in aux_masks])
+
+
+def valid_label_ranges(labels, ignore_index: int = IGNORE_INDEX):
+    """Host-side hint for the fused lm_head + loss (extension): maximal runs of rows of the flattened [B*S] batch whose
+    SHIFTED label (labels[b, s+1] at row (b, s); cambrian_llama.py:411-415) is not ignore_index.  Returns a list of
+    (row_start, row_end) python ints and the number of valid labels."""
+    lab = labels.detach().to("cpu")
+    B, S = lab.shape
+    shift = torch.full_like(lab, ignore_index)
+    shift[:, :-1] = lab[:, 1:]
+    valid = (shift != ignore_index).reshape(-1).numpy()
+    import numpy as np
+    edges = np.flatnonzero(np.diff(np.concatenate([[0], valid.astype(np.int8), [0]])))
+    ranges = [(int(a), int(b)) for a, b in zip(edges[0::2], edges[1::2])]
+    return ranges, int(valid.sum())

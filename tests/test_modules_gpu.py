@@ -448,3 +448,28 @@ def test_zero3_sharded_generate_is_token_identical():
     got = model.generate(ids.to(dev), **kw)
     assert torch.equal(ref, got)
     assert z.gathers >= 6 * cfg.num_hidden_layers
+
+
+def test_fused_loss_with_label_ranges_matches_full_rows():
+    """The collator's label-range hint only removes rows that cannot contribute: loss and every gradient must agree
+    with the all-rows fused loss."""
+    from cambrian_b200.train.collator import valid_label_ranges
+    cfg = tiny_cambrian_config()
+    cfg.fused_lm_loss = True
+    model = _build_tiny_model(cfg)
+    model.train()
+    ids, labels, attn, pos, images, masks = _tiny_batch(cfg)
+    ranges, n_valid = valid_label_ranges(labels)
+    assert 0 < sum(b - a for a, b in ranges) < labels.numel() and n_valid == sum(b - a for a, b in ranges)
+    kw = dict(input_ids=ids.to(dev), labels=labels.to(dev), attention_mask=attn.to(dev), position_ids=pos.to(dev),
+              images=[i.to(dev).bfloat16() for i in images], image_aux_attention_masks_list=[m.to(dev) for m in masks])
+    res = []
+    for lr in (None, ranges):
+        model.zero_grad(set_to_none=True)
+        out = model(**kw, label_ranges=lr, num_valid_labels=n_valid)
+        out.loss.backward()
+        res.append((out.loss.item(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    assert abs(res[0][0] - res[1][0]) < 1e-4 * abs(res[0][0])
+    assert res[0][1].keys() == res[1][1].keys()
+    for k in res[0][1]:
+        assert rel_err(res[1][1][k], res[0][1][k]) < 2e-2, k

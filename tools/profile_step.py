@@ -33,13 +33,13 @@ def main():
     model.train()
     model.get_model().gradient_checkpointing = bool(a.recompute)
     eng = TrainEngine(model)
-    hb, nv = bench.make_host_batch(cfg, a.micro_batch, 2048, 0, res)
+    hb, (nv, lr) = bench.make_host_batch(cfg, a.micro_batch, 2048, 0, res)
     db, _ = bench.to_device(hb, dev)
     pos = [cfg.image_position] * a.micro_batch
 
     def step():
         eng.zero_grad()
-        out = model(**db, num_valid_labels=nv, image_positions=pos)
+        out = model(**db, num_valid_labels=nv, image_positions=pos, label_ranges=lr)
         out.loss.backward()
         eng.step()
 
