@@ -59,6 +59,7 @@ SIGNATURES = {
     "cb_span_gather_hw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cb_span_scatter_hw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cb_window_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "cb_gemm_swiglu_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i64, _i64, _i64, _i64, _vp]),
     "cb_resample_ksize": (_i, [_i, _i]),
     "cb_resample_coeffs": (_i, [_i, _i, _vp, _vp]),
     "cb_preprocess_workspace_bytes": (_i64, [_i, _i, _i]),

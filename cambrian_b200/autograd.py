@@ -313,9 +313,7 @@ class DecoderLayerFn(torch.autograd.Function):
         attn2 = attn.view(rows, nh * hd)
         x1 = ops.gemm(attn2, o_w, residual=x2)
         h2, rstd2 = ops.rmsnorm_fwd(x1, ln2, meta["eps"], meta["hf_cast"], save_stats=True)
-        gu = ops.gemm(h2, gu_w)
-        I = gu_w.shape[0] // 2
-        act = ops.swiglu_fwd(gu[:, :I], gu[:, I:])
+        gu, act = ops.mlp_gate_up(h2, gu_w)
         out = ops.gemm(act, down_w, residual=x1)
         if keep:
             return out.view(B, S, H), (rstd1, qkv, attn, lse, x1, rstd2, gu, act)

@@ -85,6 +85,8 @@ int adamw_launch(float*, float*, float*, const void*, void*, long long, float, f
                  cudaStream_t);
 int span_gather_launch(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int span_scatter_launch(void*, const void*, int, int, int, int, int, int, cudaStream_t);
+int gemm_swiglu_bf16(const void*, const void*, void*, void*, int, int, int, long long, long long, long long, long long,
+                     cudaStream_t);
 int resample_ksize(int, int);
 void resample_coeffs(int, int, int*, int*);
 long long preprocess_workspace_bytes(int, int, int);
@@ -249,6 +251,10 @@ int cb_embed_splice_ragged(void* out, const void* embed, const void* img, const 
 }
 int cb_span_scatter(void* hidden, const void* lat, int B, int S, int H, int start, int q_side, void* stream) {
   return cb::span_scatter_launch(hidden, lat, B, S, H, start, q_side, q_side, ST(stream));
+}
+int cb_gemm_swiglu_bf16(const void* A, const void* W, void* gu_out, void* act_out, int M, int F, int K, int64_t lda,
+                        int64_t ldw, int64_t ld_gu, int64_t ld_act, void* stream) {
+  return cb::gemm_swiglu_bf16(A, W, gu_out, act_out, M, F, K, lda, ldw, ld_gu, ld_act, ST(stream));
 }
 int cb_resample_ksize(int in_size, int out_size) {
   if (in_size <= 0 || out_size <= 0) return 0;

@@ -317,30 +317,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-// delta[b, h, s] = sum_d dO[b,s,h,d] * O[b,s,h,d]   (fp32), one warp per (b, s, h)
+// delta[b, h, s] = sum_d dO[b,s,h,d] * O[b,s,h,d]   (fp32).  hd / 8 lanes (one 16-byte vector each) per (b, s, h), so a
+// warp covers 32 / (hd / 8) heads: with one warp per head only hd / 8 of the 32 lanes had work (2.2 TB/s).
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta,
                                   int B, int S, int nh, int hd, long long o_bs, long long o_ss, long long do_bs,
                                   long long do_ss) {
+  const int lph = hd >> 3;                       // lanes per head: 16 (hd 128) or 8 (hd 64)
+  const int hpw = 32 / lph;                      // heads per warp
   const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long total = (long long)B * S * nh;
-  if (w >= total) return;
-  const int h = (int)(w % nh);
-  const long long t = w / nh;
-  const int s = (int)(t % S);
-  const int b = (int)(t / S);
-  const bf16* op = o + b * o_bs + s * o_ss + (long long)h * hd;
-  const bf16* gp = d_o + b * do_bs + s * do_ss + (long long)h * hd;
+  const long long idx = w * hpw + lane / lph;    // (b, s, h) handled by this lane group
+  const int sub = lane % lph;
   float acc = 0.f;
-  for (int d = lane * 8; d < hd; d += 256) {
+  if (idx < total) {
+    const int h = (int)(idx % nh);
+    const long long t = idx / nh;
+    const int s = (int)(t % S);
+    const int b = (int)(t / S);
+    const bf16* op = o + b * o_bs + s * o_ss + (long long)h * hd + sub * 8;
+    const bf16* gp = d_o + b * do_bs + s * do_ss + (long long)h * hd + sub * 8;
     float a[8], g[8];
-    unpack8(*reinterpret_cast<const uint4*>(op + d), a);
-    unpack8(*reinterpret_cast<const uint4*>(gp + d), g);
+    unpack8(ldg_nc(op), a);
+    unpack8(ldg_nc(gp), g);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc += a[e] * g[e];
   }
-  acc = warp_sum(acc);
-  if (lane == 0) delta[((long long)b * nh + h) * S + s] = acc;
+  for (int off = lph >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (idx < total && sub == 0) {
+    const int h = (int)(idx % nh);
+    const long long t = idx / nh;
+    delta[((long long)(t / S) * nh + h) * S + (t % S)] = acc;
+  }
 }
 
 struct AttnBwdParams {
@@ -794,7 +802,7 @@ int attn_bwd_launch(const void* q, const void* k, const void* v, const void* o, 
   CB_CHECK_ARG(hd == 64 || hd == 128, "attention bwd: head_dim=%d unsupported (64 or 128)", hd);
   CB_CHECK_ARG(lse && delta && dq_acc, "attention bwd: lse / delta / dq_acc buffers are required");
   {
-    const long long warps = (long long)B * Sq * nh;
+    const long long warps = ((long long)B * Sq * nh + (256 / hd) - 1) / (256 / hd);   // 32 / (hd / 8) heads per warp
     attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>((const bf16*)o, (const bf16*)d_o, delta, B,
                                                                            Sq, nh, hd, o_bs, o_ss, do_bs, do_ss);
     CB_CUDA_LAUNCH_CHECK("attn_delta");

@@ -55,6 +55,18 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// single MUFU.EX2 (2^-inf = +0, no denormal range fix-up branches): softmax inner loops
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// single MUFU.RCP: __fdividef() adds a range check + rescale sequence (FSETP / FMUL pairs) per element
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // erf via Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): one MUFU.EX2 + one MUFU.RCP +
 // 7 FMA instead of erff's ~40-instruction polynomial, which made GELU epilogues the bottleneck of short-K GEMMs
 __device__ __forceinline__ float erf_fast(float x) {
@@ -67,8 +79,19 @@ __device__ __forceinline__ float erf_fast(float x) {
   const float r = fmaf(-t * y, __expf(-ax * ax), 1.0f);
   return copysignf(r, x);
 }
+// x * Phi(x) with the same A&S erf, constants folded for z = x / sqrt(2): 14 instructions (2 MUFU) per element —
+// GELU epilogues are ALU-bound (profiles/r01_gemm_epilogue_microbench.log), so every instruction shows
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f));
+  const float ax = fabsf(x);
+  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f));
+  float y = fmaf(t, 1.061405429f, -1.453152027f);
+  y = fmaf(t, y, 1.421413741f);
+  y = fmaf(t, y, -0.284496736f);
+  y = fmaf(t, y, 0.254829592f);
+  const float e = fast_exp2(x * x * -0.72134752044448170368f);  // exp(-x^2 / 2)
+  const float r = fmaf(-(y * t), e, 1.0f);                       // erf(|x| / sqrt(2))
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), r, hx);                                 // 0.5 x (1 + sign(x) erf(|z|))
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
@@ -82,18 +105,12 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 // tanh-GELU with tanh(u) = 1 - 2 / (1 + e^{2u}) on MUFU.EX2 / MUFU.RCP (tanhf's software path is branchy)
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  const float t = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * u));
+  const float t = 1.0f - 2.0f * fast_rcp(1.0f + fast_exp2(2.0f * 1.44269504088896340736f * u));
   return 0.5f * x * (1.0f + t);
 }
 // __fdividef: MUFU.RCP + FMUL (2 ulp) instead of the IEEE division's Newton iterations + slow-path branch
-__device__ __forceinline__ float quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
-__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-// single MUFU.EX2 (2^-inf = +0, no denormal range fix-up branches): softmax inner loops
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
+__device__ __forceinline__ float quick_gelu(float x) { return x * fast_rcp(1.0f + fast_exp2(-1.702f * 1.44269504088896340736f * x)); }
+__device__ __forceinline__ float silu(float x) { return x * fast_rcp(1.0f + fast_exp2(-1.44269504088896340736f * x)); }
 
 // 8 x bf16 <-> 8 x float through one 16-byte register quad
 struct alignas(16) bf16x8 {

@@ -334,7 +334,10 @@ __global__ void patchify_nhwc_kernel(const bf16* __restrict__ in, bf16* __restri
 // per-tap weight fetch is two conflict-free LDS.128 instead of an L2-latency LDG + 8 unpack ops (C = 1536: 150 KB of
 // weights never fit L1 next to the streamed input), (b) vertically adjacent steps re-hit their halo rows in L1.
 constexpr int DW_TY = 2, DW_TX = 4, DW_CV = 16;
-__global__ void __launch_bounds__(128, 3)
+#ifndef CB_DW_MINB
+#define CB_DW_MINB 3
+#endif
+__global__ void __launch_bounds__(128, CB_DW_MINB)
 dwconv7_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const bf16* __restrict__ bias,
                bf16* __restrict__ out, int B, int H, int W, int C, int ysplit) {
   // [tap][half][cv][4]: lanes read consecutive 16-byte words (a [cv][8] layout makes LDS.128 2-way bank-conflicted)
@@ -381,16 +384,27 @@ dwconv7_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const bf
     for (int r = 0; r < DW_TY + 6; ++r) {
       const int iy = y0 + r - 3;
       if (iy < 0 || iy >= H) continue;
+      // branch-free halo: clamp the address, select zeros afterwards — conditional loads compiled to a branch per
+      // vector and serialised the ten load latencies (ncu source view: every first use stalled on its own LDG)
+      uint4 raw[DW_TX + 6];
+      const bf16* rowp = img + (long long)iy * W * C;
+#pragma unroll
+      for (int c = 0; c < DW_TX + 6; ++c) {
+        const int ix = x0 + c - 3;
+        const int ixc = min(max(ix, 0), W - 1);
+        raw[c] = *reinterpret_cast<const uint4*>(rowp + (long long)ixc * C);
+      }
       float row[DW_TX + 6][8];
 #pragma unroll
       for (int c = 0; c < DW_TX + 6; ++c) {
         const int ix = x0 + c - 3;
-        if (ix >= 0 && ix < W) {
-          unpack8(*reinterpret_cast<const uint4*>(img + ((long long)iy * W + ix) * C), row[c]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) row[c][e] = 0.f;
-        }
+        const bool ok = ix >= 0 && ix < W;
+        uint4 v4 = raw[c];
+        v4.x = ok ? v4.x : 0u;
+        v4.y = ok ? v4.y : 0u;
+        v4.z = ok ? v4.z : 0u;
+        v4.w = ok ? v4.w : 0u;
+        unpack8(v4, row[c]);
       }
 #pragma unroll
       for (int oy = 0; oy < DW_TY; ++oy) {
@@ -813,7 +827,7 @@ int dwconv7_launch(const void* in, const void* w, const void* bias, void* out, i
   const int nchunk = (C / 8 + DW_CV - 1) / DW_CV, strips = (W + 7) / 8, steps = (H + 7) / 8;
   const long long base = (long long)nchunk * strips * B;
   // >= ~4 waves of (SMs x 3 resident blocks) when the image is tall enough, so the tail wave stays small
-  const long long want = (4LL * 3 * device_sm_count() + base - 1) / base;
+  const long long want = (4LL * CB_DW_MINB * device_sm_count() + base - 1) / base;
   const int ysplit = (int)std::max(1LL, std::min<long long>(steps, want));
   dwconv7_kernel<<<(unsigned)(base * ysplit), 128, 0, st>>>((const bf16*)in, (const bf16*)w, (const bf16*)bias,
                                                             (bf16*)out, B, H, W, C, ysplit);

@@ -39,7 +39,10 @@ struct GemmEpilogue {
   int accumulate;  // C += result
   int vec_ok;      // 16-byte vector stores are legal
   int group_m;     // tile rasterisation: 0 = m fastest over all m-blocks; g > 0 = super-rows of g m-blocks (L2 reuse of A)
+  void* aux;       // ACT_SWIGLU_PAIR: second output, silu(gate) * up, [M, N / 2] bf16
+  long long ld_aux;
 };
+constexpr int ACT_SWIGLU_PAIR = 5;  // CTA-pair kernel only: the tile's two B halves are gate rows and the matching up rows
 
 template <int BN>
 struct GemmCfg {
@@ -123,7 +126,7 @@ __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_
   const long long r_off = static_cast<long long>(b) * ep.bsr + static_cast<long long>(row) * ep.ldr;
   const bool vec = ep.vec_ok;  // N % 8 == 0 and 16-byte aligned vectors (host-checked)
   const bool has_bias = ep.bias != nullptr, has_scale = ep.colscale != nullptr;
-  const bool has_res = ep.residual != nullptr;
+  const bool has_res = ep.residual != nullptr, has_alpha = ep.alpha != 1.0f;
   // chunks are unrolled (and pipelined) in groups of INNER; the group loop itself is not unrolled to bound code size
   constexpr int INNER = NCH < CB_EPI_INNER ? NCH : CB_EPI_INNER;
   uint32_t rr[2][32];
@@ -161,7 +164,11 @@ __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_
       if (col >= N) break;
       float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[i & 1][g * 8 + j]) * ep.alpha;
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[i & 1][g * 8 + j]);
+      if (has_alpha) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= ep.alpha;
+      }
       if (has_bias) {
         float t[8];
         unpack8(qb[g], t);
@@ -205,6 +212,44 @@ __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_
       }
     }
   }
+  }
+}
+
+// LLaMA MLP first half fused (cambrian_llama.py:142-166 -> HF LlamaMLP): B = [gate_proj; up_proj] (N = 2F rows).  The
+// CTA pair's tile takes gate rows [nb*128, +128) from CTA 0's B half and up rows [F + nb*128, +128) from CTA 1's, so
+// accumulator columns [0,128) / [128,256) hold gate / up of the SAME 128 features: the epilogue writes both
+// pre-activations (saved for backward) and silu(gate) * up without a second pass over the [M, 2F] tensor.
+__device__ __forceinline__ void epilogue_swiglu_pair(const GemmEpilogue& ep, uint32_t taddr, int row, bool row_ok, int nb,
+                                                     int N, int col_half) {
+  const int F = N >> 1;
+  bf16* gu = reinterpret_cast<bf16*>(ep.C) + static_cast<long long>(row) * ep.ldc;
+  bf16* ao = reinterpret_cast<bf16*>(ep.aux) + static_cast<long long>(row) * ep.ld_aux;
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {
+    const int c = col_half * 2 + i;             // 32-column chunk of the 128 features of this tile
+    const int f0 = nb * 128 + c * 32;           // feature index
+    if (f0 >= F) break;                         // warp-uniform
+    uint32_t rg[32], ru[32];
+    tmem_ld32(taddr + c * 32, rg);
+    tmem_ld32(taddr + 128 + c * 32, ru);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int f = f0 + g * 8;
+      if (f >= F) break;
+      float a[8], u[8], o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // round to bf16 first: the separate kernels (and the reference) apply silu to the STORED bf16 pre-activations
+        a[j] = __bfloat162float(__float2bfloat16(__uint_as_float(rg[g * 8 + j])));
+        u[j] = __bfloat162float(__float2bfloat16(__uint_as_float(ru[g * 8 + j])));
+        o[j] = silu(a[j]) * u[j];
+      }
+      *reinterpret_cast<uint4*>(gu + f) = pack8(a);
+      *reinterpret_cast<uint4*>(gu + F + f) = pack8(u);
+      *reinterpret_cast<uint4*>(ao + f) = pack8(o);
+    }
   }
 }
 
@@ -445,7 +490,8 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int mb_, nb_;
         tile_to_mn(r, m_blocks, n_blocks, ep.group_m, mb_, nb_);
         const int m0 = mb_ * (2 * BM) + static_cast<int>(rank) * BM;
-        const int n0 = nb_ * BN + static_cast<int>(rank) * Cfg::HALF_N;
+        const int n0 = (ACT == ACT_SWIGLU_PAIR) ? nb_ * Cfg::HALF_N + static_cast<int>(rank) * (N >> 1)
+                                                : nb_ * BN + static_cast<int>(rank) * Cfg::HALF_N;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -530,7 +576,10 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
-      epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64));
+      if constexpr (ACT == ACT_SWIGLU_PAIR)
+        epilogue_swiglu_pair(ep, taddr, row, row_ok, nb_, N, col_half);
+      else
+        epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // leader's barrier
@@ -716,6 +765,7 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
   ep.residual = static_cast<const bf16*>(residual);
   ep.ldr = ldr; ep.bsr = bsr;
   ep.alpha = alpha; ep.act = act; ep.out_fp32 = out_fp32; ep.accumulate = accumulate;
+  ep.aux = nullptr; ep.ld_aux = 0;
   const int cvec = out_fp32 ? 4 : 8;
   bool vec = (N % 8 == 0) && (ldc % cvec == 0) && (bsc % cvec == 0) &&
              ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
@@ -738,6 +788,35 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
     case 128: return dispatch_major<128>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
     default:  return dispatch_major<64>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
   }
+}
+
+// gate/up projection + SwiGLU in one CTA-pair GEMM.  A [M, K] (lda), W = [gate_proj; up_proj] [2F, K] (ldw);
+// gu_out [M, 2F] (ld_gu) receives the bf16 pre-activations, act_out [M, F] (ld_act) silu(gate) * up.
+int gemm_swiglu_bf16(const void* A, const void* W, void* gu_out, void* act_out, int M, int F, int K, long long lda,
+                     long long ldw, long long ld_gu, long long ld_act, cudaStream_t stream) {
+  CB_CHECK_ARG(M > 0 && F > 0 && K > 0, "gemm_swiglu: empty problem M=%d F=%d K=%d", M, F, K);
+  CB_CHECK_ARG(A && W && gu_out && act_out, "gemm_swiglu: null operand");
+  CB_CHECK_ARG(F % 128 == 0, "gemm_swiglu: F=%d must be a multiple of 128 (one tile pairs 128 gate with 128 up columns)", F);
+  CB_CHECK_ARG(ld_gu % 8 == 0 && ld_act % 8 == 0 && ((reinterpret_cast<uintptr_t>(gu_out) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(act_out) & 15u) == 0),
+               "gemm_swiglu: outputs must be 16-byte aligned with ld %% 8 == 0");
+  const int N = 2 * F;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tmA, A, K, M, 1, lda, 0, BM))) return rc;
+  if ((rc = make_tmap_bf16_3d(&tmB, W, K, N, 1, ldw, 0, 128))) return rc;
+  GemmEpilogue ep;
+  ep.C = gu_out; ep.ldc = ld_gu; ep.bsc = 0;
+  ep.bias = nullptr; ep.colscale = nullptr; ep.residual = nullptr; ep.ldr = 0; ep.bsr = 0;
+  ep.alpha = 1.0f; ep.act = ACT_SWIGLU_PAIR; ep.out_fp32 = 0; ep.accumulate = 0; ep.vec_ok = 1;
+  ep.aux = act_out; ep.ld_aux = ld_act;
+  static int gm = -1;
+  if (gm < 0) {
+    const char* e = getenv("CB_GEMM_GROUP_M");
+    gm = e ? atoi(e) : 2048;
+  }
+  ep.group_m = gm / (2 * BM);
+  return launch_gemm2<256, false, false, ACT_SWIGLU_PAIR>(tmA, tmB, M, N, K, 1, ep, stream);
 }
 
 }  // namespace cb

@@ -195,9 +195,7 @@ class CBLlamaDecoderLayer(nn.Module):
         x1 = ops.gemm(attn.view(rows, nh * hd), a.o_proj.weight, residual=x2)
         h2 = ops.rmsnorm_fwd(x1, self.post_attention_layernorm.weight, self.post_attention_layernorm.variance_epsilon,
                              rt["hf_cast"])
-        gu = ops.gemm(h2, gu_w)
-        I = gu_w.shape[0] // 2
-        act = ops.swiglu_fwd(gu[:, :I], gu[:, I:])
+        _, act = ops.mlp_gate_up(h2, gu_w)
         return ops.gemm(act, m.down_proj.weight, residual=x1).view(B, S, H)
 
 

@@ -522,3 +522,37 @@ def preprocess_image(img_u8, size: int, pad_rgb, mean, std, return_u8: bool = Fa
     check(lib.cb_preprocess_image(ptr(img_u8), H, W, size, ctypes.addressof(pad), ctypes.addressof(m), ctypes.addressof(sd),
                                   ptr(out), ptr(u8), ptr(ws), nbytes, stream()), "cb_preprocess_image")
     return (out, u8) if return_u8 else out
+
+
+def gemm_swiglu(x2d, w_gu, gu_out=None, act_out=None):
+    """(gu, act) = fused gate/up projection + SwiGLU: gu = x @ [gate; up]^T [M, 2F], act = silu(gu[:, :F]) * gu[:, F:]."""
+    _require_cuda_bf16(x2d, w_gu)
+    M, K = x2d.shape
+    F2 = w_gu.shape[0]
+    if F2 % 256 or x2d.stride(1) != 1 or w_gu.stride(1) != 1:
+        raise ValueError("gemm_swiglu: need contiguous rows and F % 128 == 0")
+    F = F2 // 2
+    gu = gu_out if gu_out is not None else torch.empty((M, F2), dtype=torch.bfloat16, device=x2d.device)
+    act = act_out if act_out is not None else torch.empty((M, F), dtype=torch.bfloat16, device=x2d.device)
+    check(_lib.load().cb_gemm_swiglu_bf16(ptr(x2d), ptr(w_gu), ptr(gu), ptr(act), M, F, K, x2d.stride(0), w_gu.stride(0),
+                                          gu.stride(0), act.stride(0), stream()), "cb_gemm_swiglu_bf16")
+    return gu, act
+
+
+import os as _os
+
+_FUSED_SWIGLU = _os.environ.get("CB_FUSED_SWIGLU", "1") != "0"
+
+
+def mlp_gate_up(h2d, w_gu):
+    """gate/up projection + SwiGLU: the fused CTA-pair kernel when the problem fills the SM pairs for >= 3 waves (the
+    same rule cb_gemm_bf16 uses to pick that kernel) and F % 128 == 0, otherwise GEMM followed by the SwiGLU kernel."""
+    M = h2d.shape[0]
+    F2 = w_gu.shape[0]
+    I = F2 // 2
+    pairs = max(_lib.load().cb_sm_count() // 2, 1)
+    if (_FUSED_SWIGLU and F2 % 256 == 0 and ((M + 255) // 256) * (F2 // 256) >= 3 * pairs and h2d.is_contiguous()
+            and w_gu.is_contiguous()):
+        return gemm_swiglu(h2d, w_gu)
+    gu = gemm(h2d, w_gu)
+    return gu, swiglu_fwd(gu[:, :I], gu[:, I:])

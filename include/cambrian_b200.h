@@ -179,6 +179,11 @@ int cb_window_gather(const void* feat, void* out, int B, int q_side, int r, int 
  * zeros if src == -1 (padding), newline if src == INT32_MIN, img[-2 - src] otherwise; rows = B * max_len. */
 int cb_embed_splice_ragged(void* out, const void* embed, const void* img, const void* newline, const int32_t* src,
                            int64_t rows, int H, void* stream);
+/* LLaMA MLP first half in one launch (HF LlamaMLP, reached from cambrian_llama.py:142-166): W = [gate_proj; up_proj]
+ * [2F, K]; gu_out [M, 2F] = A W^T (bf16 pre-activations, saved for backward), act_out [M, F] = silu(gate) * up.
+ * F % 128 == 0.  CTA-pair tcgen05 kernel whose tile pairs 128 gate columns with the matching 128 up columns. */
+int cb_gemm_swiglu_bf16(const void* A, const void* W, void* gu_out, void* act_out, int M, int F, int K, int64_t lda,
+                        int64_t ldw, int64_t ld_gu, int64_t ld_act, void* stream);
 /* Image preprocessing on the GPU — replaces, per tower, the host chain of `process_images`
  * (mm_utils.py:186-201): expand2square(img, int(mean*255)) -> PIL Image.resize((R,R)) [bicubic, antialiased, uint8,
  * bit-exact with Pillow's Resample.c] -> x/255 -> (x-mean)/std.  img: device uint8 [H,W,3] RGB; out: bf16 [3,R,R];

@@ -37,6 +37,10 @@ def test_gemm_cta_pair_kernel(capsys):
     _run("probe1", "gemm_2cta", capsys, 24)
 
 
+def test_gemm_fused_gate_up_swiglu(capsys):
+    _run("probe1", "gemm_swiglu", capsys, 5)
+
+
 def test_sva_window_attention_fwd_bwd(capsys):
     _run("probe1", "sva", capsys, 4)
 

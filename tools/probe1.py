@@ -125,6 +125,38 @@ def group_gemm_2cta():
         print(f"perf cublas M={M} N={N} K={K}: {ms:.4f} ms {2 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
+def group_gemm_swiglu():
+    """Fused gate/up projection + SwiGLU (cb_gemm_swiglu_bf16) vs GEMM + the stand-alone SwiGLU kernel and fp32 torch."""
+    import torch.nn.functional as F_
+    for (M, F, K) in [(256, 128, 64), (512, 256, 256), (300, 1024, 192), (1000, 384, 520), (4096, 2048, 1024)]:
+        x = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(2 * F, K, device=dev) * 0.05).bfloat16()
+        gu, act = ops.gemm_swiglu(x, w)
+        ref_gu = (x.float() @ w.float().t())
+        e1 = rel_err(gu, ref_gu)
+        g16 = gu.float()
+        ref_act = F_.silu(g16[:, :F]) * g16[:, F:]
+        e2 = rel_err(act, ref_act)
+        gu2 = ops.gemm(x, w)
+        act2 = ops.swiglu_fwd(gu2[:, :F], gu2[:, F:])
+        same = bool(torch.equal(gu, gu2)) and (act.float() - act2.float()).abs().max().item() <= 2 ** -7 * act2.float().abs().max().item()
+        ok = e1 < 1e-2 and e2 < 1e-2 and same
+        print(f"gemm_swiglu M={M} F={F} K={K} gu={e1:.2e} act={e2:.2e} same_as_unfused={same} {'OK' if ok else 'FAIL'}", flush=True)
+    M, F, K = 8192, 14336, 4096
+    x = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(2 * F, K, device=dev) * 0.02).bfloat16()
+    gu = torch.empty(M, 2 * F, device=dev, dtype=torch.bfloat16)
+    act = torch.empty(M, F, device=dev, dtype=torch.bfloat16)
+    t_f = timeit(lambda: ops.gemm_swiglu(x, w, gu, act))
+
+    def unfused():
+        ops.gemm(x, w, out=gu)
+        ops.swiglu_fwd(gu[:, :F], gu[:, F:])
+    t_u = timeit(unfused)
+    print(f"perf gate/up+swiglu M={M} F={F} K={K}: fused {t_f:.4f} ms ({4 * M * F * K / t_f / 1e9:.0f} TFLOP/s)  "
+          f"unfused {t_u:.4f} ms", flush=True)
+
+
 def group_gemm_perf():
     for (M, N, K) in [(8192, 8192, 8192), (8192, 14336, 4096), (8192, 4096, 14336), (4096, 4096, 4096),
                       (2304, 1024, 1024)]:
