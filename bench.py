@@ -362,6 +362,7 @@ def main():
     model.train()
     model.get_model().gradient_checkpointing = bool(args.recompute)
     engine = TrainEngine(model, lr=4e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    engine.defer_param_sync = os.environ.get("CB_DEFER_PARAM_SYNC", "1") != "0"   # towers overlap the optimizer tail
     n_train = sum(p.numel() for p in engine.params)
     n_tower = sum(p.numel() for t in model.get_model().vision_tower_aux_list for p in t.parameters())
 

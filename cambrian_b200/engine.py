@@ -109,6 +109,13 @@ class TrainEngine:
         self._updated = [False] * len(self.buckets)
         self._handles = {}
         self._opt_stream = None
+        self._params_pending = False
+        self._towers_trainable = any("vision_tower" in n for n in self.names)
+        # opt-in (bench / training loops): skip the end-of-step wait on the optimizer stream and let the model wait just
+        # before its first trainable module; anyone reading parameters right after step() must call wait_for_params()
+        self.defer_param_sync = False
+        if hasattr(model, "prepare_inputs_labels_for_multimodal"):
+            model._cb_param_sync = self.wait_for_params
 
     # ---- per-step protocol ---------------------------------------------------------------------------------------
     def zero_grad(self):
@@ -231,7 +238,19 @@ class TrainEngine:
                 self._update_bucket(b, side_stream=False)
         self.step_count += 1
         if self._opt_stream is not None:
-            torch.cuda.current_stream().wait_stream(self._opt_stream)   # next forward sees every updated parameter
+            if self.defer_param_sync and hasattr(self.model, "_cb_param_sync") and not self._towers_trainable:
+                # the frozen towers of the next forward read no trainable parameter: let them overlap the tail of the
+                # optimizer (last buckets: embeddings, connector); the model calls wait_for_params() before the first
+                # trainable module runs (cambrian_arch.prepare_inputs_labels_for_multimodal / forward without images)
+                self._params_pending = True
+            else:
+                torch.cuda.current_stream().wait_stream(self._opt_stream)   # next forward sees every updated parameter
+
+    def wait_for_params(self):
+        """Make the current stream wait for optimizer updates still running on the side stream (no-op otherwise)."""
+        if self._params_pending:
+            self._params_pending = False
+            torch.cuda.current_stream().wait_stream(self._opt_stream)
 
     # ---- convenience ---------------------------------------------------------------------------------------------
     def train_step(self, **batch):

@@ -218,6 +218,8 @@ class CambrianMetaForCausalLM(ABC):
         q_num = cfg.image_token_len
         fh = fw = int(q_num ** 0.5)
         feats = self.encode_images(images)
+        if getattr(self, "_cb_param_sync", None) is not None:
+            self._cb_param_sync()
         feats_final = masks_final = ctx_final = None
         if cfg.mm_projector_type == "sva":
             aux = [getattr(model, f"mm_projector_aux_{i}")(f.to(torch.bfloat16)) for i, f in enumerate(feats)]
@@ -317,6 +319,8 @@ class CambrianMetaForCausalLM(ABC):
         model = self.get_model()
         towers = model.get_vision_tower_aux_list()
         if towers is None or images is None or input_ids.shape[1] == 1:                          # :345-346
+            if getattr(self, "_cb_param_sync", None) is not None:
+                self._cb_param_sync()
             return input_ids, position_ids, attention_mask, past_key_values, None, labels, None, None, None, None
         cfg = model.config
         bs = images[0].shape[0]
@@ -353,6 +357,9 @@ class CambrianMetaForCausalLM(ABC):
         img_start = torch.tensor(starts, dtype=torch.int32).to(input_ids.device, non_blocking=True)
 
         feats = self.encode_images(images)                                                      # :366
+        sync = getattr(self, "_cb_param_sync", None)
+        if sync is not None:
+            sync()            # TrainEngine: optimizer tail of the previous step overlapped the (frozen) towers above
         feats_final = masks_final = ctx_final = None
         if cfg.mm_projector_type == "sva":
             aux = [getattr(model, f"mm_projector_aux_{i}")(f.to(torch.bfloat16)) for i, f in enumerate(feats)]   # :372-379

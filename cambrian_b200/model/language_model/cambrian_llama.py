@@ -408,6 +408,8 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
         the flattened [B*S] positions outside of which every SHIFTED label is ignore_index (train/collator.py:
         valid_label_ranges) — the fused loss then skips the vocabulary GEMMs of rows that cannot contribute."""
         feats = masks = final_size = ctx_feat = None
+        if inputs_embeds is not None and getattr(self, "_cb_param_sync", None) is not None:
+            self._cb_param_sync()
         if inputs_embeds is None:
             (input_ids, position_ids, attention_mask, past_key_values, inputs_embeds, labels, feats, masks, final_size,
              ctx_feat) = self.prepare_inputs_labels_for_multimodal(

@@ -286,7 +286,7 @@ def test_engine_overlapped_optimizer_matches_serial():
     whole-buffer update: same kernels on the same values, only the schedule differs."""
     from cambrian_b200.engine import TrainEngine
     results = []
-    for overlap in (True, False):
+    for overlap in (True, False, "defer"):
         cfg = tiny_cambrian_config()
         cfg.fused_lm_loss = True
         model = _build_tiny_model(cfg)
@@ -295,7 +295,8 @@ def test_engine_overlapped_optimizer_matches_serial():
         batch = dict(input_ids=ids.to(dev), labels=labels.to(dev), attention_mask=attn.to(dev), position_ids=pos.to(dev),
                      images=[i.to(dev).bfloat16() for i in images],
                      image_aux_attention_masks_list=[m.to(dev) for m in masks])
-        eng = TrainEngine(model, lr=1e-3, bucket_mb=8.0, overlap=overlap)
+        eng = TrainEngine(model, lr=1e-3, bucket_mb=8.0, overlap=bool(overlap))
+        eng.defer_param_sync = overlap == "defer"    # towers of the next step overlap the optimizer tail
         losses = []
         for _ in range(3):
             eng.zero_grad()
@@ -310,6 +311,8 @@ def test_engine_overlapped_optimizer_matches_serial():
     # embedding-row gradients use bf16 atomics (order-dependent rounding), so allow last-bit differences there
     assert rel_err(results[0][0], results[1][0]) < 2e-2
     assert rel_err(results[0][1], results[1][1]) < 1e-3
+    assert rel_err(results[2][0], results[1][0]) < 2e-2 and rel_err(results[2][1], results[1][1]) < 1e-3
+    assert results[2][2][0] == results[1][2][0]
 
 
 def test_engine_step_and_greedy_generate():
