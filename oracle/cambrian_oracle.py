@@ -13,8 +13,10 @@ modules.  Pinning status (see tests/test_oracle_pin.py, tests/golden/make_golden
   * CLIP ViT, DINOv2 ViT, LLaMA decoder layer — pinned against the installed `transformers` implementations
     the reference delegates to (clip_encoder.py:47, dino_encoder.py:81, cambrian_llama.py:23-24).
   * SigLIP ViT and ConvNeXt-XXL trunks — the reference delegates to timm 0.9.16 via open_clip, which is NOT
-    installed and cannot be fetched: restated from the published timm definitions; PARITY UNPINNED for these
-    two trunks (structure cross-checked against transformers' SiglipVisionModel / ConvNextModel only).
+    installed and cannot be fetched.  Restated from the published timm definitions and pinned against the
+    independent `transformers` implementations of the same architectures (SiglipVisionModel, ConvNextModel) with
+    weights mapped name by name (tests/test_oracle_pin.py).  What stays unpinned against the reference's own
+    dependency is one choice only: the GELU flavour timm 0.9.16 applies in the SigLIP MLP (a config field here).
 """
 from __future__ import annotations
 
@@ -451,7 +453,7 @@ def dinov2_vit(sd, cfg, images):
 def siglip_vit(sd, cfg, images):
     """SiglipVisionTower._forward, siglip_encoder.py:95-99 -> timm VisionTransformer.forward_features of
     vit_so400m_patch14_siglip_384 (class_token=False, learned pos, fused qkv with bias, erf-GELU, final norm,
-    LN eps 1e-6).  timm parameter names.  PARITY UNPINNED (timm not installed)."""
+    LN eps 1e-6).  timm parameter names.  Pinned against transformers' SiglipVisionModel (timm itself is not installed)."""
     x = F.conv2d(images, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=cfg["patch_size"])
     x = x.flatten(2).transpose(1, 2) + sd["pos_embed"]
     heads = cfg["num_attention_heads"]
@@ -476,7 +478,8 @@ def convnext_trunk(sd, cfg, images):
     """CLIPConvNextTower._forward, clip_convnext_encoder.py:121-144 -> timm ConvNeXt stem + stages
     (convnext_xxlarge: depths 3-4-30-3, dims 384-768-1536-3072; block = dwconv7x7 -> LN -> fc1 -> GELU -> fc2
     -> gamma -> +residual; downsample = LN2d + conv2x2/2).  Returns the last stage (or all 4, multi-stage)
-    bilinearly resized to the interp grid (:99-119) as [B, N, C].  PARITY UNPINNED (timm not installed)."""
+    bilinearly resized to the interp grid (:99-119) as [B, N, C].  Pinned against transformers' ConvNextModel (timm itself
+    is not installed)."""
     x = F.conv2d(images, sd["stem.0.weight"], sd["stem.0.bias"], stride=4)
     x = _ln2d(sd, "stem.1", x)
     outs = []

@@ -208,3 +208,65 @@ def test_prepare_dynamic_matches_reference_golden():
         assert np.array_equal(m.numpy(), z[f"final_m{i}"])
     # right-padded position ids of the branch (cambrian_arch.py:582-584) restart at 0 for every sample
     assert pos[0, :5].tolist() == [0, 1, 2, 3, 4]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SigLIP ViT and ConvNeXt trunks: the reference takes them from timm 0.9.16 via open_clip (not installed, cannot be
+# fetched).  The restatements are pinned instead against the independent `transformers` implementations of the same
+# published architectures with the weights mapped name by name — this fixes the block structure, the fused-qkv split,
+# LN placement / eps, layer scale, stem / downsample arithmetic; what remains unpinned is only timm's choice of GELU
+# flavour for the SigLIP MLP (a config field of the restatement and of the CUDA tower).
+# ---------------------------------------------------------------------------------------------------------------
+def test_oracle_siglip_matches_transformers_siglip_vision_model():
+    from transformers import SiglipVisionConfig, SiglipVisionModel
+    cfg = SiglipVisionConfig(hidden_size=96, intermediate_size=160, num_hidden_layers=2, num_attention_heads=4, image_size=56,
+                             patch_size=14, layer_norm_eps=1e-6, hidden_act="gelu_pytorch_tanh")
+    torch.manual_seed(0)
+    m = SiglipVisionModel(cfg).eval()
+    hf = m.state_dict()
+    sd = {"patch_embed.proj.weight": hf["vision_model.embeddings.patch_embedding.weight"],
+          "patch_embed.proj.bias": hf["vision_model.embeddings.patch_embedding.bias"],
+          "pos_embed": hf["vision_model.embeddings.position_embedding.weight"][None],
+          "norm.weight": hf["vision_model.post_layernorm.weight"], "norm.bias": hf["vision_model.post_layernorm.bias"]}
+    for i in range(cfg.num_hidden_layers):
+        h, q = f"vision_model.encoder.layers.{i}.", f"blocks.{i}."
+        for a, b in (("layer_norm1", "norm1"), ("layer_norm2", "norm2"), ("self_attn.out_proj", "attn.proj"),
+                     ("mlp.fc1", "mlp.fc1"), ("mlp.fc2", "mlp.fc2")):
+            sd[q + b + ".weight"], sd[q + b + ".bias"] = hf[h + a + ".weight"], hf[h + a + ".bias"]
+        sd[q + "attn.qkv.weight"] = torch.cat([hf[h + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0)
+        sd[q + "attn.qkv.bias"] = torch.cat([hf[h + f"self_attn.{n}_proj.bias"] for n in "qkv"], 0)
+    x = torch.randn(2, 3, 56, 56)
+    with torch.no_grad():
+        want = m(pixel_values=x).last_hidden_state                        # post-layernorm tokens, no head
+        got = O.siglip_vit(sd, dict(patch_size=14, num_attention_heads=4, num_hidden_layers=2, act="gelu_tanh"), x)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_oracle_convnext_matches_transformers_convnext_model():
+    from transformers import ConvNextConfig, ConvNextModel
+    depths, dims = [1, 1, 2, 1], [16, 32, 64, 128]
+    cfg = ConvNextConfig(num_channels=3, patch_size=4, num_stages=4, hidden_sizes=dims, depths=depths, hidden_act="gelu",
+                         layer_norm_eps=1e-6, layer_scale_init_value=0.5, drop_path_rate=0.0)
+    torch.manual_seed(0)
+    m = ConvNextModel(cfg).eval()
+    hf = m.state_dict()
+    sd = {"stem.0.weight": hf["embeddings.patch_embeddings.weight"], "stem.0.bias": hf["embeddings.patch_embeddings.bias"],
+          "stem.1.weight": hf["embeddings.layernorm.weight"], "stem.1.bias": hf["embeddings.layernorm.bias"]}
+    for s, depth in enumerate(depths):
+        h, p = f"encoder.stages.{s}.", f"stages.{s}."
+        if s > 0:
+            sd[p + "downsample.0.weight"], sd[p + "downsample.0.bias"] = hf[h + "downsampling_layer.0.weight"], hf[h + "downsampling_layer.0.bias"]
+            sd[p + "downsample.1.weight"], sd[p + "downsample.1.bias"] = hf[h + "downsampling_layer.1.weight"], hf[h + "downsampling_layer.1.bias"]
+        for b in range(depth):
+            hb, q = f"{h}layers.{b}.", f"{p}blocks.{b}."
+            sd[q + "conv_dw.weight"], sd[q + "conv_dw.bias"] = hf[hb + "dwconv.weight"], hf[hb + "dwconv.bias"]
+            sd[q + "norm.weight"], sd[q + "norm.bias"] = hf[hb + "layernorm.weight"], hf[hb + "layernorm.bias"]
+            sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"] = hf[hb + "pwconv1.weight"], hf[hb + "pwconv1.bias"]
+            sd[q + "mlp.fc2.weight"], sd[q + "mlp.fc2.bias"] = hf[hb + "pwconv2.weight"], hf[hb + "pwconv2.bias"]
+            sd[q + "gamma"] = hf[hb + "layer_scale_parameter"]
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        out = m(pixel_values=x, output_hidden_states=True)
+        want = out.hidden_states[-1]                                       # last stage feature map [B, C, 2, 2]
+        got = O.convnext_trunk(sd, dict(depths=depths, interp=4), x)       # 2 x 2 grid -> identity resize
+    torch.testing.assert_close(got, want.flatten(2).transpose(1, 2), rtol=1e-4, atol=1e-5)

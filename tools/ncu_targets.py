@@ -16,9 +16,11 @@ torch.manual_seed(0)
 a = torch.randn(8192, 4096, device=dev).bfloat16()
 w = torch.randn(28672, 4096, device=dev).bfloat16()
 out = torch.empty(8192, 28672, device=dev, dtype=torch.bfloat16)
+act = torch.empty(8192, 14336, device=dev, dtype=torch.bfloat16)
 for _ in range(2):
     ops.gemm(a, w, out=out)                       # heuristic -> CTA-pair kernel
     ops.gemm(a, w, out=out, force_bn=256)         # single-CTA kernel for comparison
+    ops.gemm_swiglu(a, w, out, act)               # fused gate/up + SwiGLU (what the decoder layer launches)
 for rs in ([1, 1, 1, 1], [1, 1, 1, 4]):
     B, q = 32, 24
     qq = torch.randn(B * q * q, 1024, device=dev).bfloat16()
