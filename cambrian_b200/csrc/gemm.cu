@@ -17,6 +17,7 @@
 //                                   activation-heavy epilogue such as GELU keeps up with short-K mainloops)
 // The TMEM accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
+#include <cstring>
 #include <cudaTypedefs.h>
 #include <mutex>
 #include <cstdlib>
@@ -39,6 +40,7 @@ struct GemmEpilogue {
   int accumulate;  // C += result
   int vec_ok;      // 16-byte vector stores are legal
   int group_m;     // tile rasterisation: 0 = m fastest over all m-blocks; g > 0 = super-rows of g m-blocks (L2 reuse of A)
+  int tma_store;   // bf16 output without accumulate: tiles leave through smem staging + TMA stores (tmC / tmAux)
   void* aux;       // ACT_SWIGLU_PAIR: second output, silu(gate) * up, [M, N / 2] bf16
   long long ld_aux;
 };
@@ -51,7 +53,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128 — powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 1024 /*barriers*/ + 32768 /*store staging*/;
 };
 
 // activation selected at COMPILE time: a per-element runtime switch (plus slow-path erff / tanhf) made the epilogue of
@@ -86,6 +88,39 @@ __device__ __forceinline__ void tile_to_mn(int r, int m_blocks, int n_blocks, in
 
 // Epilogue of one accumulator tile for the 32-column chunks [c_begin, c_end) owned by this warp:
 // tcgen05.ld -> alpha, bias, activation, LayerScale, residual, accumulate -> bf16 / fp32 stores.
+// Output staging for TMA stores.  Each epilogue warp owns two 2 KB buffers holding a [32 rows][32 bf16] tile in the
+// SWIZZLE_64B layout of the output tensor map (16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)), fills one
+// with st.shared (conflict-free per quarter-warp) and lets lane 0 issue the bulk store.  Direct st.global from the
+// tcgen05.ld register layout writes 16 bytes to each of 32 different rows per instruction; those uncoalesced stores
+// share the L1 data path with the TMA operand fills and cost the gate/up GEMM 8 % once its output grew by a third
+// (profiles/r01_gemm_store_path.log).
+struct StageRing {
+  uint32_t base;  // this warp's 4 KB
+  int k;          // tiles issued so far
+};
+__device__ __forceinline__ void stage_store_tile(StageRing& ring, int lane, const CUtensorMap* tm, int col0, int row0,
+                                                 int b, const uint4 (&v)[4]) {
+  const uint32_t buf = ring.base + (ring.k & 1) * 2048;
+  if (ring.k >= 2) {  // the store issued two tiles ago used this buffer: wait until the engine has read it
+    if (lane == 0) bulk_wait_group_read1();
+    __syncwarp();
+  }
+  const uint32_t dst = buf + lane * 64;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + ((j ^ sw) << 4)), "r"(v[j].x), "r"(v[j].y),
+                 "r"(v[j].z), "r"(v[j].w)
+                 : "memory");
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm, buf, col0, row0, b);
+    bulk_commit_group();
+  }
+  ++ring.k;
+}
+
 #ifndef CB_EPI_INNER
 #define CB_EPI_INNER 1  // measured: 1 beats 2 and 4 (profiles/r01_gemm_epilogue_microbench.log) — code size matters more than ILP
 #endif
@@ -117,7 +152,8 @@ __device__ __noinline__ void epilogue_chunk_scalar(const GemmEpilogue& ep, const
 
 template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_t taddr, int row, bool row_ok, int b,
-                                                 int n0, int N, int c_begin) {
+                                                 int n0, int N, int c_begin, StageRing& ring, const CUtensorMap* tmC,
+                                                 int row0, int lane) {
   // One warp drains NCH 32-column chunks of its 32 accumulator rows, software-pipelined: the tcgen05.ld of chunk i+1 and
   // the bias / column-scale / residual vectors of chunk i are in flight while chunk i's arithmetic runs — with only two
   // epilogue warps per scheduler nothing else hides those latencies.
@@ -153,6 +189,48 @@ __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_
     }
     tmem_ld_wait();
     if (i + 1 < INNER && col0 + 32 < N) tmem_ld32(taddr + (c + 1) * 32, rr[(i + 1) & 1]);
+    if (ep.tma_store) {
+      // whole warp participates (rows / columns past the edge are clipped by the store engine)
+      uint4 tile[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = col0 + g * 8;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[i & 1][g * 8 + j]);
+        if (has_alpha) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= ep.alpha;
+        }
+        if (col < N) {
+          if (has_bias) {
+            float t[8];
+            unpack8(qb[g], t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += t[j];
+          }
+          if (ACT != 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = apply_act<ACT>(v[j]);
+          }
+          if (has_scale) {
+            float t[8];
+            unpack8(qs[g], t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= t[j];
+          }
+          if (has_res && row_ok) {
+            float t[8];
+            unpack8(qr[g], t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += t[j];
+          }
+        }
+        tile[g] = pack8(v);
+      }
+      stage_store_tile(ring, lane, tmC, col0, row0, b, tile);
+      continue;
+    }
     if (!row_ok) continue;
     if (!vec) {
       epilogue_chunk_scalar<ACT>(ep, rr[i & 1], c_off, r_off, col0, N);
@@ -220,7 +298,8 @@ __device__ __forceinline__ void epilogue_columns(const GemmEpilogue& ep, uint32_
 // accumulator columns [0,128) / [128,256) hold gate / up of the SAME 128 features: the epilogue writes both
 // pre-activations (saved for backward) and silu(gate) * up without a second pass over the [M, 2F] tensor.
 __device__ __forceinline__ void epilogue_swiglu_pair(const GemmEpilogue& ep, uint32_t taddr, int row, bool row_ok, int nb,
-                                                     int N, int col_half) {
+                                                     int N, int col_half, StageRing& ring, const CUtensorMap* tmC,
+                                                     const CUtensorMap* tmAux, int row0, int lane) {
   const int F = N >> 1;
   bf16* gu = reinterpret_cast<bf16*>(ep.C) + static_cast<long long>(row) * ep.ldc;
   bf16* ao = reinterpret_cast<bf16*>(ep.aux) + static_cast<long long>(row) * ep.ld_aux;
@@ -233,6 +312,26 @@ __device__ __forceinline__ void epilogue_swiglu_pair(const GemmEpilogue& ep, uin
     tmem_ld32(taddr + c * 32, rg);
     tmem_ld32(taddr + 128 + c * 32, ru);
     tmem_ld_wait();
+    if (ep.tma_store) {
+      uint4 tg[4], tu[4], to[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float a[8], u[8], o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a[j] = __bfloat162float(__float2bfloat16(__uint_as_float(rg[g * 8 + j])));
+          u[j] = __bfloat162float(__float2bfloat16(__uint_as_float(ru[g * 8 + j])));
+          o[j] = silu(a[j]) * u[j];
+        }
+        tg[g] = pack8(a);
+        tu[g] = pack8(u);
+        to[g] = pack8(o);
+      }
+      stage_store_tile(ring, lane, tmC, f0, row0, 0, tg);
+      stage_store_tile(ring, lane, tmC, F + f0, row0, 0, tu);
+      stage_store_tile(ring, lane, tmAux, f0, row0, 0, to);
+      continue;
+    }
     if (!row_ok) continue;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -256,7 +355,7 @@ __device__ __forceinline__ void epilogue_swiglu_pair(const GemmEpilogue& ep, uin
 template <int BN, bool A_MN, bool B_MN, int ACT>
 __global__ void __launch_bounds__(320, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  int M, int N, int K, int batch, GemmEpilogue ep) {
+                  const __grid_constant__ CUtensorMap tmC, int M, int N, int K, int batch, GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -382,6 +481,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int col_half = (warp - 2) >> 2;  // warps 2-5: first half of the tile's columns, warps 6-9: second half
     int acc = 0;
     uint32_t acc_phase = 0;
+    StageRing ring{bar_base + 1024u + static_cast<uint32_t>(warp - 2) * 4096u, 0};
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
@@ -395,7 +495,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
-      epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64));
+      epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64), ring, &tmC,
+                                m0 + lane_grp * 32, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -406,6 +507,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   }
 
+  if (warp >= 2 && lane == 0) bulk_wait_group0();  // staged output tiles fully written before the CTA retires
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -428,12 +530,13 @@ struct Gemm2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024 + 32768;  // align slack, barriers, store staging
 };
 
 template <int BN, bool A_MN, bool B_MN, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
-gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux, int M, int N,
                        int K, int batch, GemmEpilogue ep) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -563,6 +666,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int col_half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    StageRing ring{bar_base + 1024u + static_cast<uint32_t>(warp - 2) * 4096u, 0};
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
@@ -577,9 +681,10 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
       if constexpr (ACT == ACT_SWIGLU_PAIR)
-        epilogue_swiglu_pair(ep, taddr, row, row_ok, nb_, N, col_half);
+        epilogue_swiglu_pair(ep, taddr, row, row_ok, nb_, N, col_half, ring, &tmC, &tmAux, m0 + lane_grp * 32, lane);
       else
-        epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64));
+        epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64), ring, &tmC,
+                                  m0 + lane_grp * 32, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // leader's barrier
@@ -590,6 +695,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   }
 
+  if (warp >= 2 && lane == 0) bulk_wait_group0();  // staged output tiles fully written before the CTA retires
   tc_fence_before();
   cluster_sync_all();  // the leader's MMAs read the peer's smem: nobody may exit (or free TMEM) before both are done
   tc_fence_after();
@@ -642,9 +748,39 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return CB_OK;
 }
 
+// bf16 output [batch, rows, cols] (ld elements per row): 32 x 32 store boxes, SWIZZLE_64B (see StageRing)
+static int make_tmap_out(CUtensorMap* out, void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld_elems,
+                         uint64_t batch_stride_elems) {
+  auto fn = get_encode_fn();
+  if (!fn) return set_error(CB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t bs = (batch > 1) ? batch_stride_elems * 2 : ld_elems * 2 * (rows ? rows : 1);
+  cuuint64_t strides[2] = {ld_elems * 2, bs};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    cudaFree(0);
+  }
+  if (r != CUDA_SUCCESS) return set_error(CB_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed (%d)", (int)r);
+  return CB_OK;
+}
+
+static bool tma_store_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CB_GEMM_TMA_STORE");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 template <int BN, bool A_MN, bool B_MN, int ACT>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int batch,
-                       const GemmEpilogue& ep, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M, int N, int K,
+                       int batch, const GemmEpilogue& ep, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_bf16_tcgen05<BN, A_MN, B_MN, ACT>;
   static bool attr_set = false;
@@ -655,14 +791,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, in
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * batch;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, batch, ep);
+  kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, batch, ep);
   CB_CUDA_LAUNCH_CHECK("gemm_bf16_tcgen05");
   return CB_OK;
 }
 
 template <int BN, bool A_MN, bool B_MN, int ACT>
-static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int batch,
-                        const GemmEpilogue& ep, cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmAux,
+                        int M, int N, int K, int batch, const GemmEpilogue& ep, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
   auto kern = gemm_bf16_tcgen05_2cta<BN, A_MN, B_MN, ACT>;
   static bool attr_set = false;
@@ -674,25 +810,26 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, i
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN) * batch;
   const int pairs = device_sm_count() / 2;
   const int clusters = tiles < pairs ? tiles : pairs;
-  kern<<<2 * clusters, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, batch, ep);
+  kern<<<2 * clusters, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmAux, M, N, K, batch, ep);
   CB_CUDA_LAUNCH_CHECK("gemm_bf16_tcgen05_2cta");
   return CB_OK;
 }
 
-static int dispatch_2cta(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+static int dispatch_2cta(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M,
+                         int N, int K,
                          int batch, const GemmEpilogue& ep, cudaStream_t stream) {
   if (!a_mn && !b_mn) {  // forward layout: the only one that carries a fused activation
     switch (ep.act) {
-      case 1: return launch_gemm2<256, false, false, 1>(tmA, tmB, M, N, K, batch, ep, stream);
-      case 2: return launch_gemm2<256, false, false, 2>(tmA, tmB, M, N, K, batch, ep, stream);
-      case 3: return launch_gemm2<256, false, false, 3>(tmA, tmB, M, N, K, batch, ep, stream);
-      case 4: return launch_gemm2<256, false, false, 4>(tmA, tmB, M, N, K, batch, ep, stream);
-      default: return launch_gemm2<256, false, false, 0>(tmA, tmB, M, N, K, batch, ep, stream);
+      case 1: return launch_gemm2<256, false, false, 1>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
+      case 2: return launch_gemm2<256, false, false, 2>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
+      case 3: return launch_gemm2<256, false, false, 3>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
+      case 4: return launch_gemm2<256, false, false, 4>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
+      default: return launch_gemm2<256, false, false, 0>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
     }
   }
-  if (!a_mn && b_mn) return launch_gemm2<256, false, true, 0>(tmA, tmB, M, N, K, batch, ep, stream);
-  if (a_mn && !b_mn) return launch_gemm2<256, true, false, 0>(tmA, tmB, M, N, K, batch, ep, stream);
-  return launch_gemm2<256, true, true, 0>(tmA, tmB, M, N, K, batch, ep, stream);
+  if (!a_mn && b_mn) return launch_gemm2<256, false, true, 0>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
+  if (a_mn && !b_mn) return launch_gemm2<256, true, false, 0>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
+  return launch_gemm2<256, true, true, 0>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
 }
 
 // CB_GEMM_2CTA=0 disables the CTA-pair kernel (read once)
@@ -706,20 +843,21 @@ static bool two_cta_enabled() {
 }
 
 template <int BN>
-static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N,
+static int dispatch_major(int a_mn, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, int M,
+                          int N,
                           int K, int batch, const GemmEpilogue& ep, cudaStream_t stream) {
   if (!a_mn && !b_mn) {
     switch (ep.act) {
-      case 1: return launch_gemm<BN, false, false, 1>(tmA, tmB, M, N, K, batch, ep, stream);
-      case 2: return launch_gemm<BN, false, false, 2>(tmA, tmB, M, N, K, batch, ep, stream);
-      case 3: return launch_gemm<BN, false, false, 3>(tmA, tmB, M, N, K, batch, ep, stream);
-      case 4: return launch_gemm<BN, false, false, 4>(tmA, tmB, M, N, K, batch, ep, stream);
-      default: return launch_gemm<BN, false, false, 0>(tmA, tmB, M, N, K, batch, ep, stream);
+      case 1: return launch_gemm<BN, false, false, 1>(tmA, tmB, tmC, M, N, K, batch, ep, stream);
+      case 2: return launch_gemm<BN, false, false, 2>(tmA, tmB, tmC, M, N, K, batch, ep, stream);
+      case 3: return launch_gemm<BN, false, false, 3>(tmA, tmB, tmC, M, N, K, batch, ep, stream);
+      case 4: return launch_gemm<BN, false, false, 4>(tmA, tmB, tmC, M, N, K, batch, ep, stream);
+      default: return launch_gemm<BN, false, false, 0>(tmA, tmB, tmC, M, N, K, batch, ep, stream);
     }
   }
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true, 0>(tmA, tmB, M, N, K, batch, ep, stream);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false, 0>(tmA, tmB, M, N, K, batch, ep, stream);
-  return launch_gemm<BN, true, true, 0>(tmA, tmB, M, N, K, batch, ep, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, 0>(tmA, tmB, tmC, M, N, K, batch, ep, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, 0>(tmA, tmB, tmC, M, N, K, batch, ep, stream);
+  return launch_gemm<BN, true, true, 0>(tmA, tmB, tmC, M, N, K, batch, ep, stream);
 }
 
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int batch, long long lda,
@@ -774,6 +912,13 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
   if (bias) vec = vec && ((reinterpret_cast<uintptr_t>(bias) & 15u) == 0);
   if (colscale) vec = vec && ((reinterpret_cast<uintptr_t>(colscale) & 15u) == 0);
   ep.vec_ok = vec ? 1 : 0;
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  ep.tma_store = 0;
+  if (vec && !out_fp32 && !accumulate && tma_store_enabled()) {
+    if ((rc = make_tmap_out(&tmC, C, N, M, batch, ldc, bsc))) return rc;
+    ep.tma_store = 1;
+  }
   {
     static int gm = -1;  // CB_GEMM_GROUP_M: rows of the L2 super-row (default 2048 rows)
     if (gm < 0) {
@@ -782,11 +927,11 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
     }
     ep.group_m = gm / (use_2cta ? 2 * BM : BM);
   }
-  if (use_2cta) return dispatch_2cta(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
+  if (use_2cta) return dispatch_2cta(a_mn, b_mn, tmA, tmB, tmC, M, N, K, batch, ep, stream);
   switch (bn) {
-    case 256: return dispatch_major<256>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
-    case 128: return dispatch_major<128>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
-    default:  return dispatch_major<64>(a_mn, b_mn, tmA, tmB, M, N, K, batch, ep, stream);
+    case 256: return dispatch_major<256>(a_mn, b_mn, tmA, tmB, tmC, M, N, K, batch, ep, stream);
+    case 128: return dispatch_major<128>(a_mn, b_mn, tmA, tmB, tmC, M, N, K, batch, ep, stream);
+    default:  return dispatch_major<64>(a_mn, b_mn, tmA, tmB, tmC, M, N, K, batch, ep, stream);
   }
 }
 
@@ -810,13 +955,22 @@ int gemm_swiglu_bf16(const void* A, const void* W, void* gu_out, void* act_out, 
   ep.bias = nullptr; ep.colscale = nullptr; ep.residual = nullptr; ep.ldr = 0; ep.bsr = 0;
   ep.alpha = 1.0f; ep.act = ACT_SWIGLU_PAIR; ep.out_fp32 = 0; ep.accumulate = 0; ep.vec_ok = 1;
   ep.aux = act_out; ep.ld_aux = ld_act;
+  CUtensorMap tmC, tmAux;
+  memset(&tmC, 0, sizeof(tmC));
+  memset(&tmAux, 0, sizeof(tmAux));
+  ep.tma_store = 0;
+  if (tma_store_enabled()) {
+    if ((rc = make_tmap_out(&tmC, gu_out, N, M, 1, ld_gu, 0))) return rc;
+    if ((rc = make_tmap_out(&tmAux, act_out, F, M, 1, ld_act, 0))) return rc;
+    ep.tma_store = 1;
+  }
   static int gm = -1;
   if (gm < 0) {
     const char* e = getenv("CB_GEMM_GROUP_M");
     gm = e ? atoi(e) : 2048;
   }
   ep.group_m = gm / (2 * BM);
-  return launch_gemm2<256, false, false, ACT_SWIGLU_PAIR>(tmA, tmB, M, N, K, 1, ep, stream);
+  return launch_gemm2<256, false, false, ACT_SWIGLU_PAIR>(tmA, tmB, tmC, tmAux, M, N, K, 1, ep, stream);
 }
 
 }  // namespace cb
