@@ -453,12 +453,14 @@ def main():
         roof = dict(bound="tensor", kernel="gemm_bf16_tcgen05", achieved=ach, peak=tf_sustained, unit="TFLOP/s",
                     frac=ach / tf_sustained, traffic=None, launches_timed=n, share_of_step=tms / ms,
                     peak_source=f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)")
-    # ncu --set full DRAM traffic of the dominant GEMM launch (decoder gate/up projection, M=8192 N=28672 K=4096):
-    # profiles/r01_kernels_ncu_summary.txt; algorithmic bytes of that launch = (M*K + N*K + M*N)*2 = 0.772 GB
+    # ncu --set full DRAM traffic of the dominant GEMM launch — the decoder's fused gate/up projection + SwiGLU
+    # (cb_gemm_swiglu_bf16, M=8192 F=14336 K=4096): profiles/r01_kernels_v2_ncu_summary.txt; algorithmic bytes of that
+    # launch = (M*K + 2F*K + M*2F + M*F) * 2 = 1.007 GB
     if roof is not None:
-        roof["traffic"] = 1.036081e9 + 0.452051e9
-        roof["traffic_note"] = ("dram read+write bytes of ONE launch of the dominant shape M=8192 N=28672 K=4096 "
-                                "(algorithmic 0.772e9 B; 2.67e9 B before tile rasterisation); ncu capture under profiles/")
+        roof["traffic"] = 1.546132e9 + 0.683987e9
+        roof["traffic_note"] = ("dram read+write bytes of ONE launch of the dominant kernel: fused gate/up + SwiGLU GEMM "
+                                "M=8192 F=14336 K=4096 (algorithmic 1.007e9 B; tensor pipe 97.7 % active in the same "
+                                "capture); ncu summary under profiles/")
     roof_sva = None
     if not args.small:
         # second headline metric (BASELINE.json "SVA HBM GB/s"): the fused window-attention kernel alone, on inputs larger
