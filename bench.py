@@ -512,6 +512,7 @@ def main():
                                         f"loss and gradients identical; MFU counts executed FLOPs only)", "l2_policy": "inputs larger than L2 (16 GB weights streamed per pass)"},
                 gpu_launches=int(launches), host_enqueue_ms_per_step=round(host_enqueue_ms, 1), loss=float(loss),
                 peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+                peak_reserved_gb=round(torch.cuda.max_memory_reserved() / 2 ** 30, 1),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(h2d_bytes), d2h_bytes_per_step=4),
                 clocks=sampler.summary(), roofline=roof, roofline_sva=roof_sva,
                 model_tflops_per_gpu=(model_tf / world) if model_tf else None,
