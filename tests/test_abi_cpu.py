@@ -65,3 +65,47 @@ def test_product_never_imports_the_oracle():
         src = p.read_text()
         assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), \
             f"{p} references the oracle — the product path must not depend on test infrastructure"
+
+
+def test_argument_validation_of_later_entry_points_without_gpu(lib):
+    """Every check below fails before the first CUDA call, so it runs on the CPU-only builder too."""
+    one = ctypes.c_void_p(16)                                   # non-null, 16-byte aligned dummy pointer (never dereferenced)
+    rc = lib.cb_gemm_swiglu_bf16(one, one, one, one, 256, 100, 64, 64, 64, 200, 100, None)
+    assert rc == 1 and b"multiple of 128" in lib.cb_last_error()
+    rc = lib.cb_gemm_swiglu_bf16(None, one, one, one, 256, 128, 64, 64, 64, 256, 128, None)
+    assert rc == 1 and b"null" in lib.cb_last_error()
+    rc = lib.cb_window_gather(one, one, 1, 4, 2, 64, 0, 5, 0, 4, None)        # crop rows [0, 5) of a 4 x 4 query grid
+    assert rc == 1 and b"crop" in lib.cb_last_error()
+    rc = lib.cb_window_gather(one, one, 1, 4, 2, 60, 0, 4, 0, 4, None)        # channels not a multiple of 8
+    assert rc == 1
+    rc = lib.cb_span_gather_hw(one, one, 1, 20, 64, 5, 4, 4, None)            # 4 x (4 + 1) = 20 rows from position 5 of 20
+    assert rc == 1 and b"outside sequence" in lib.cb_last_error()
+    rc = lib.cb_span_scatter_hw(one, one, 1, 64, 64, 5, 0, 4, None)           # empty grid
+    assert rc == 1
+    rc = lib.cb_embed_splice_ragged(one, one, one, one, one, 0, 64, None)
+    assert rc == 1 and b"no rows" in lib.cb_last_error()
+    rc = lib.cb_preprocess_image(None, 10, 10, 8, None, None, None, None, None, None, 0, None)
+    assert rc == 1 and b"null" in lib.cb_last_error()
+    pad = (ctypes.c_int32 * 3)(0, 0, 0)
+    f3 = (ctypes.c_float * 3)(0.5, 0.5, 0.5)
+    need = lib.cb_preprocess_workspace_bytes(480, 640, 336)
+    assert need > 640 * 336 * 3
+    rc = lib.cb_preprocess_image(one, 480, 640, 336, ctypes.addressof(pad), ctypes.addressof(f3), ctypes.addressof(f3), one, None,
+                                 one, need - 1, None)
+    assert rc == 1 and b"workspace" in lib.cb_last_error()
+    assert lib.cb_preprocess_workspace_bytes(0, 640, 336) == 0
+    assert lib.cb_resample_ksize(640, 336) == 9 and lib.cb_resample_ksize(336, 336) == 5
+
+
+def test_resample_coefficients_are_normalised(lib):
+    """Fixed-point rows sum to 2^22 (+- rounding) and stay inside the source image — host-only entry point."""
+    for (src, dst) in ((640, 336), (336, 336), (100, 384), (1500, 1024)):
+        ks = lib.cb_resample_ksize(src, dst)
+        bounds = (ctypes.c_int32 * (2 * dst))()
+        kk = (ctypes.c_int32 * (ks * dst))()
+        assert lib.cb_resample_coeffs(src, dst, ctypes.addressof(bounds), ctypes.addressof(kk)) == 0
+        for x in range(dst):
+            x0, n = bounds[2 * x], bounds[2 * x + 1]
+            assert 0 <= x0 and x0 + n <= src and 0 < n <= ks
+            row = kk[x * ks:(x + 1) * ks]
+            assert abs(sum(row) - (1 << 22)) <= ks and all(v == 0 for v in row[n:])
