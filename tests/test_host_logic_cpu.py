@@ -367,3 +367,61 @@ def test_resample_coefficients_reproduce_pillow_bit_exact(hw, R):
     want = np.asarray(img.resize((R, R)))
     got = _pil_equivalent_resize(arr, R, pad)
     assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------------------------ dynamic-branch host helpers
+def test_product_unmask_and_unpad_match_reference_golden():
+    """cambrian_b200.model.cambrian_arch.unmask_attention_mask / unpad_image / unpad_bounds (host code of the dynamic
+    branch) against the fixtures generated from the reference's own functions (tests/golden/dynamic.npz)."""
+    from cambrian_b200.model import cambrian_arch as A
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "dynamic.npz"))
+    n = 0
+    for k in z.files:
+        if not k.startswith("unmask_"):
+            continue
+        wh, side = k[len("unmask_"):].rsplit("_", 1)
+        w, h = map(int, wh.split("x"))
+        side = int(side)
+        got = A.unmask_attention_mask(torch.ones(1, side, side, dtype=torch.bool), (w, h))
+        assert np.array_equal(got.numpy(), z[k]), k
+        y0, y1, x0, x1 = A.unpad_bounds(side, side, (w, h))
+        assert (y1 - y0, x1 - x0) == tuple(z["unpad_" + k[len("unmask_"):]]), k
+        t = torch.arange(side * side).view(1, side, side, 1)
+        assert torch.equal(A.unpad_image(t, (w, h)), t[:, y0:y1, x0:x1])
+        n += 1
+    assert n == 15
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cambrian"), reason="reference tree only exists in the build container")
+def test_product_unmask_and_unpad_match_live_reference_on_random_sizes():
+    from oracle import ref_shim
+    from cambrian_b200.model import cambrian_arch as A
+    ref = ref_shim.ref_module("cambrian.model.cambrian_arch")
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        w, h = int(rng.integers(16, 4000)), int(rng.integers(16, 4000))
+        side = int(rng.choice([16, 24, 27, 48, 96]))
+        want = ref.unmask_attention_mask(torch.ones(1, side, side, dtype=torch.bool), (w, h))
+        got = A.unmask_attention_mask(torch.ones(1, side, side, dtype=torch.bool), (w, h))
+        assert torch.equal(got, want), (w, h, side)
+        t = torch.arange(side * side).view(1, side, side, 1)
+        if 0 in ref.unpad_image(t, (w, h)).shape:
+            continue                                   # degenerate aspect ratios crop everything away in the reference too
+        assert torch.equal(A.unpad_image(t, (w, h)), ref.unpad_image(t, (w, h))), (w, h, side)
+
+
+def test_valid_label_ranges_cover_exactly_the_valid_shifted_labels():
+    from cambrian_b200.train.collator import valid_label_ranges
+    rng = np.random.default_rng(9)
+    for _ in range(50):
+        B, S = int(rng.integers(1, 5)), int(rng.integers(2, 40))
+        lab = torch.from_numpy(np.where(rng.random((B, S)) < 0.5, -100, rng.integers(0, 100, (B, S))))
+        ranges, n = valid_label_ranges(lab)
+        shift = torch.full_like(lab, -100)
+        shift[:, :-1] = lab[:, 1:]
+        mask = torch.zeros(B * S, dtype=torch.bool)
+        for a, b in ranges:
+            assert a < b
+            mask[a:b] = True
+        assert torch.equal(mask, (shift != -100).view(-1)) and n == int(mask.sum())
+        assert all(ranges[i][1] < ranges[i + 1][0] for i in range(len(ranges) - 1))       # maximal, ordered runs
