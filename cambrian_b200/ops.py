@@ -3,6 +3,9 @@ include/cambrian_b200.h.  Tensors are torch CUDA tensors used purely as device b
 launches the hand-written sm_100a kernel on the current torch stream.  No fallbacks."""
 from __future__ import annotations
 
+import ctypes
+import os
+
 import torch
 
 from . import _lib
@@ -494,7 +497,6 @@ def embed_splice_ragged(embed_w, img, newline, src, batch: int, max_len: int):
 
 def resample_coeffs(in_size: int, out_size: int):
     """Host-side Pillow-compatible bicubic coefficient tables: (bounds int32 [out, 2], kk int32 [out, ksize])."""
-    import ctypes
     lib = _lib.load()
     ks = lib.cb_resample_ksize(in_size, out_size)
     bounds = torch.empty((out_size, 2), dtype=torch.int32)
@@ -506,7 +508,6 @@ def resample_coeffs(in_size: int, out_size: int):
 def preprocess_image(img_u8, size: int, pad_rgb, mean, std, return_u8: bool = False):
     """img_u8: CUDA uint8 [H, W, 3] RGB -> bf16 [3, size, size] = normalise(resize(expand2square(img))) with Pillow's
     exact uint8 bicubic arithmetic (mm_utils.py:186-201).  Optionally also returns the resized uint8 image."""
-    import ctypes
     if not img_u8.is_cuda or img_u8.dtype != torch.uint8 or img_u8.dim() != 3 or img_u8.shape[2] != 3:
         raise ValueError("preprocess_image: expected a CUDA uint8 [H, W, 3] tensor")
     img_u8 = img_u8.contiguous()
@@ -539,9 +540,8 @@ def gemm_swiglu(x2d, w_gu, gu_out=None, act_out=None):
     return gu, act
 
 
-import os as _os
-
-_FUSED_SWIGLU = _os.environ.get("CB_FUSED_SWIGLU", "1") != "0"
+# CB_FUSED_SWIGLU=0 falls back to GEMM + stand-alone SwiGLU kernel (A/B switch used for profiles/, both are CUDA paths)
+_FUSED_SWIGLU = os.environ.get("CB_FUSED_SWIGLU", "1") != "0"
 
 
 def mlp_gate_up(h2d, w_gu):
