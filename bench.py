@@ -184,7 +184,23 @@ class KernelTimer:
             timer.events.append(("sva_bwd", float(byts), s, e))
             return r
 
+        gs0 = ops_mod.gemm_swiglu
+
+        def gemm_swiglu(x2d, w_gu, gu_out=None, act_out=None):
+            # the decoder's fused gate/up projection + SwiGLU (the dominant launch): 2 * M * 2F * K FLOP
+            if not timer.enabled:
+                return gs0(x2d, w_gu, gu_out, act_out)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = gs0(x2d, w_gu, gu_out, act_out)
+            e.record()
+            M, K = x2d.shape
+            timer.events.append(("gemm", 2.0 * M * w_gu.shape[0] * K, s, e))
+            timer.shapes.append(((M, w_gu.shape[0]), K, False, False, "swiglu_pair", False, False, len(timer.events) - 1))
+            return out
+
         ops_mod.gemm, ops_mod.sva_window_attn_fwd, ops_mod.sva_window_attn_bwd = gemm, sva_f, sva_b
+        ops_mod.gemm_swiglu = gemm_swiglu
 
     def shape_table(self, top=24):
         """Per-shape GEMM time / rate inside the timed step (CB_BENCH_SHAPES=1 prints it to stderr)."""
