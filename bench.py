@@ -215,6 +215,26 @@ class KernelTimer:
         return [f"{ms:9.2f} ms {n:5d}x {fl / ms / 1e9:7.0f} TF/s  out={k[0]} K={k[1]} a_mn={int(k[2])} b_mn={int(k[3])} "
                 f"act={k[4]} bias={int(k[5])} res={int(k[6])}" for k, (fl, ms, n) in rows]
 
+    def dominant(self):
+        """The fused gate/up + SwiGLU GEMM launches alone (the kernel `roofline.traffic` was captured on): per-launch
+        algorithmic FLOP / average CUDA-event duration."""
+        fl = ms = 0.0
+        n = 0
+        shape = None
+        for rec in self.shapes:
+            if rec[4] != "swiglu_pair":
+                continue
+            _, work, s, e = self.events[rec[-1]]
+            fl += work
+            ms += s.elapsed_time(e)
+            n += 1
+            shape = (rec[0], rec[1])
+        if n == 0 or ms <= 0:
+            return None
+        return dict(kernel="gemm_bf16_tcgen05_2cta<256,0,0,swiglu_pair> (cb_gemm_swiglu_bf16)",
+                    shape=f"M={shape[0][0]} 2F={shape[0][1]} K={shape[1]}", launches_timed=n,
+                    flop_per_launch=fl / n, avg_launch_ms=ms / n, achieved=fl / (ms / 1000.0) / 1e12)
+
     def totals(self):
         agg = {}
         for kind, work, s, e in self.events:
@@ -473,6 +493,13 @@ def main():
     # (cb_gemm_swiglu_bf16, M=8192 F=14336 K=4096): profiles/r01_kernels_v2_ncu_summary.txt; algorithmic bytes of that
     # launch = (M*K + 2F*K + M*2F + M*F) * 2 = 1.007 GB
     if roof is not None:
+        try:
+            dom = timer.dominant()
+            if dom is not None:
+                dom["frac"] = dom["achieved"] / tf_sustained
+                roof["dominant_launch"] = dom
+        except Exception as exc:  # never let optional reporting break the bench line
+            roof["dominant_launch"] = {"error": str(exc)}
         roof["traffic"] = 1.546132e9 + 0.683987e9
         roof["traffic_note"] = ("dram read+write bytes of ONE launch of the dominant kernel: fused gate/up + SwiGLU GEMM "
                                 "M=8192 F=14336 K=4096 (algorithmic 1.007e9 B; tensor pipe 97.7 % active in the same "
