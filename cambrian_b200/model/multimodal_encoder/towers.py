@@ -185,7 +185,12 @@ def _vit_blocks(x, blocks, heads, act, eps):
         a = ops.attn_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal=False)
         x2 = ops.gemm(a.view(B * T, D), blk["proj_w"], bias=blk["proj_b"], colscale=blk.get("ls1"), residual=x2)
         h = ops.layernorm_fwd(x2, blk["ln2_w"], blk["ln2_b"], eps)
-        m = ops.gemm(h, blk["fc1_w"], bias=blk["fc1_b"], act=act)
+        if "win_w" in blk:   # DINOv2-giant: SwiGLU FFN (HF Dinov2SwiGLUFFN: chunk(weights_in(x)) -> silu(x1) * x2 -> weights_out)
+            gu = ops.gemm(h, blk["win_w"], bias=blk["win_b"])
+            F_ = gu.shape[1] // 2
+            m = ops.swiglu_fwd(gu[:, :F_], gu[:, F_:])
+        else:
+            m = ops.gemm(h, blk["fc1_w"], bias=blk["fc1_b"], act=act)
         x2 = ops.gemm(m, blk["fc2_w"], bias=blk["fc2_b"], colscale=blk.get("ls2"), residual=x2)
     return x2.view(B, T, D)
 
@@ -285,13 +290,16 @@ class DinoVisionTower(BaseVisionTower):
         "facebook/dinov2-large": dict(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, mlp_ratio=4),
         "facebook/dinov2-base": dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, mlp_ratio=4),
         "facebook/dinov2-small": dict(hidden_size=384, num_hidden_layers=12, num_attention_heads=6, mlp_ratio=4),
+        # the release tower (scripts/cambrian/finetune_cambrian_8b.sh:17-18: facebook/dinov2-giant-res378): SwiGLU FFN
+        "facebook/dinov2-giant": dict(hidden_size=1536, num_hidden_layers=40, num_attention_heads=24, mlp_ratio=4,
+                                      swiglu=True),
     }
 
     def __init__(self, vision_tower, args, delay_load=False):
         super().__init__(vision_tower, args, delay_load)
         base, res, interp = _parse_res_interp(vision_tower)
-        if "dinov2-giant" in base:
-            raise NotImplementedError("DINOv2-giant (SwiGLU FFN) is the release-config tower; BASELINE names ViT-L/14")
+        if "dinov2-giant-imagenet1k" in base:
+            raise NotImplementedError("facebook/dinov2-giant-imagenet1k-1-layer (classifier checkpoint) is unused by Cambrian-1")
         key = next((k for k in self.CONFIGS if base.startswith(k)), None)
         if key is None:
             raise ValueError(f"Unknown vision tower: {vision_tower}")
@@ -331,8 +339,13 @@ class DinoVisionTower(BaseVisionTower):
             l.layer_scale1.lambda1 = nn.Parameter(torch.ones(D))
             l.norm2 = nn.LayerNorm(D, eps=1e-6)
             l.mlp = nn.Module()
-            l.mlp.fc1 = nn.Linear(D, I)
-            l.mlp.fc2 = nn.Linear(I, D)
+            if c.get("swiglu", False):      # HF Dinov2SwiGLUFFN parameter names
+                Fh = (int(I * 2 / 3) + 7) // 8 * 8
+                l.mlp.weights_in = nn.Linear(D, 2 * Fh)
+                l.mlp.weights_out = nn.Linear(Fh, D)
+            else:
+                l.mlp.fc1 = nn.Linear(D, I)
+                l.mlp.fc2 = nn.Linear(I, D)
             l.layer_scale2 = nn.Module()
             l.layer_scale2.lambda1 = nn.Parameter(torch.ones(D))
             layers.append(l)
@@ -360,14 +373,18 @@ class DinoVisionTower(BaseVisionTower):
                  pos=pos[0].contiguous(), ln_w=vt.layernorm.weight, ln_b=vt.layernorm.bias, blocks=[])
         for l in vt.encoder.layer:
             a = l.attention.attention
-            g["blocks"].append(dict(
+            blk = dict(
                 ln1_w=l.norm1.weight, ln1_b=l.norm1.bias,
                 qkv_w=torch.cat([a.query.weight, a.key.weight, a.value.weight], 0).contiguous(),
                 qkv_b=torch.cat([a.query.bias, a.key.bias, a.value.bias], 0).contiguous(),
                 proj_w=l.attention.output.dense.weight, proj_b=l.attention.output.dense.bias,
-                ls1=l.layer_scale1.lambda1, ln2_w=l.norm2.weight, ln2_b=l.norm2.bias,
-                fc1_w=l.mlp.fc1.weight, fc1_b=l.mlp.fc1.bias, fc2_w=l.mlp.fc2.weight, fc2_b=l.mlp.fc2.bias,
-                ls2=l.layer_scale2.lambda1))
+                ls1=l.layer_scale1.lambda1, ln2_w=l.norm2.weight, ln2_b=l.norm2.bias, ls2=l.layer_scale2.lambda1)
+            if hasattr(l.mlp, "weights_in"):
+                blk.update(win_w=l.mlp.weights_in.weight, win_b=l.mlp.weights_in.bias, fc2_w=l.mlp.weights_out.weight,
+                           fc2_b=l.mlp.weights_out.bias)
+            else:
+                blk.update(fc1_w=l.mlp.fc1.weight, fc1_b=l.mlp.fc1.bias, fc2_w=l.mlp.fc2.weight, fc2_b=l.mlp.fc2.bias)
+            g["blocks"].append(blk)
         self._gpu = g
 
     def _run(self, images):

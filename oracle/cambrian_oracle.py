@@ -30,6 +30,27 @@ IMAGE_TOKEN_INDEX = -200
 
 
 # ------------------------------------------------------------------------------------------------
+# numerics modes
+# ------------------------------------------------------------------------------------------------
+# Every function below is dtype- and device-agnostic plain torch, so the same restatement serves as
+#   * the fp32 oracle ("truth"): fp32 state dict + fp32 inputs, and
+#   * the EAGER-bf16 oracle: `eager_bf16(sd)` + bf16 inputs.  torch then rounds to bf16 after every op exactly as the
+#     reference does when it runs its eager PyTorch path in bf16 (fp32 accumulation inside each matmul, fp32 islands
+#     where the reference upcasts: RMSNorm statistics, softmax of the decoder attention, token-grid interpolation,
+#     the logits before the loss).  This is the reference's ACTUAL arithmetic on a GPU, and therefore the yardstick for
+#     the CUDA path:  err(CUDA, fp32 oracle)  <=  slack * err(eager-bf16 oracle, fp32 oracle)   per tensor.
+# Both modes may run on any torch device (the tests use the GPU box's device for the full-size cases so the oracle
+# finishes in seconds; that is the checker running on torch/cuBLAS, never the product).
+def eager_bf16(sd):
+    """bf16 copy of a (fp32) state dict: the weights the reference holds when it runs in bf16."""
+    return {k: (v.detach().to(torch.bfloat16) if v.is_floating_point() else v.detach()) for k, v in sd.items()}
+
+
+def to_device(sd, device):
+    return {k: v.to(device) for k, v in sd.items()}
+
+
+# ------------------------------------------------------------------------------------------------
 # small building blocks
 # ------------------------------------------------------------------------------------------------
 def _lin(sd, name, x, bias=True):
@@ -79,7 +100,8 @@ def sva_layer(sd, p, queries, ctx, feats, masks, heads=16):
         ks.append(_lin(sd, p + f"cross_attn.k_proj_{i}.1", _ln(sd, p + f"cross_attn.k_proj_{i}.0", f), bias=False))
         vs.append(_lin(sd, p + f"cross_attn.v_proj_{i}.1", _ln(sd, p + f"cross_attn.v_proj_{i}.0", f), bias=False))
         m = masks[i] if masks is not None and masks[i] is not None else None
-        ms.append(torch.ones(n, f.shape[1], dtype=torch.bool) if m is None else m.view(n, -1).bool())
+        ms.append(torch.ones(n, f.shape[1], dtype=torch.bool, device=f.device) if m is None
+                  else m.view(n, -1).bool().to(f.device))
     hidden = q.shape[-1]
     hd = hidden // heads
     Q = _lin(sd, p + "cross_attn.q_proj.1", _ln(sd, p + "cross_attn.q_proj.0", q), bias=False)
@@ -156,7 +178,7 @@ def splice(sd, input_ids, image_features):
 # A9-A11 — LLaMA decoder with SVA insertion, lm_head, loss
 # ------------------------------------------------------------------------------------------------
 def rope_cos_sin(position_ids, head_dim, theta):
-    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32, device=position_ids.device) / head_dim))
     fr = position_ids[..., None].float() * inv                               # [B,S,hd/2]
     emb = torch.cat([fr, fr], -1)
     return emb.cos(), emb.sin()
@@ -165,6 +187,7 @@ def rope_cos_sin(position_ids, head_dim, theta):
 def apply_rope(x, cos, sin):
     """x [B,h,S,hd]; HF rotate_half convention."""
     x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    cos, sin = cos.to(x.dtype), sin.to(x.dtype)     # HF LlamaRotaryEmbedding returns cos/sin in the activation dtype
     return x * cos[:, None] + torch.cat([-x2, x1], -1) * sin[:, None]
 
 
@@ -181,10 +204,10 @@ def llama_layer(sd, p, x, cos, sin, attn_mask_2d, cfg):
     k = k.repeat_interleave(nh // nkv, 1)
     v = v.repeat_interleave(nh // nkv, 1)
     s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
-    causal = torch.ones(S, S, dtype=torch.bool).tril()
+    causal = torch.ones(S, S, dtype=torch.bool, device=x.device).tril()
     allow = causal[None, None]
     if attn_mask_2d is not None:
-        allow = allow & attn_mask_2d.bool()[:, None, None, :]
+        allow = allow & attn_mask_2d.bool().to(x.device)[:, None, None, :]
     s = s.masked_fill(~allow, torch.finfo(s.dtype).min)                      # HF additive-min mask semantics
     a = (torch.softmax(s.float(), -1).to(s.dtype) @ v).transpose(1, 2).reshape(B, S, H)
     x = x + F.linear(a, sd[p + "self_attn.o_proj.weight"])
@@ -444,7 +467,11 @@ def dinov2_vit(sd, cfg, images):
                  cfg["num_attention_heads"])
         x = x + a * sd[q + "layer_scale1.lambda1"]
         h = _ln(sd, q + "norm2", x, eps)
-        m = _lin(sd, q + "mlp.fc2", F.gelu(_lin(sd, q + "mlp.fc1", h)))
+        if (q + "mlp.weights_in.weight") in sd:     # dinov2-giant: HF Dinov2SwiGLUFFN
+            x1, x2 = _lin(sd, q + "mlp.weights_in", h).chunk(2, -1)
+            m = _lin(sd, q + "mlp.weights_out", F.silu(x1) * x2)
+        else:
+            m = _lin(sd, q + "mlp.fc2", F.gelu(_lin(sd, q + "mlp.fc1", h)))
         x = x + m * sd[q + "layer_scale2.lambda1"]
     x = _ln(sd, "layernorm", x, eps)
     return bilinear_tokens(x[:, 1:], cfg.get("interp", x.shape[1] - 1))

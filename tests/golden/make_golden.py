@@ -66,6 +66,15 @@ SVA_CASES = {
     "sva_inllm": dict(q_dim=256, rs=[1, 2, 1, 3], layers=1, n=32, seed=13),
 }
 
+# full-size cases (BASELINE config 1: 576 queries over 4 x 24 x 24 x 1024 grids, connector depth 3; the release grids
+# [1,1,1,4]; one in-LLM layer at Llama-3-8B width).  Outputs are stored subsampled (rows 0::(4 * q_dim / 1024) as fp16) together with the
+# fp32 row sums of ALL rows, so the fixtures stay small while every row is covered.
+SVA_FULL_CASES = {
+    "sva_config1": dict(q_dim=1024, rs=[1, 1, 1, 1], layers=3, n=576, seed=51),
+    "sva_config1_r4": dict(q_dim=1024, rs=[1, 1, 1, 4], layers=3, n=576, seed=52),
+    "sva_inllm_4096": dict(q_dim=4096, rs=[1, 1, 1, 4], layers=1, n=576, seed=53),
+}
+
 DYN = dict(sizes=[(800, 400), (336, 336), (200, 500)], q=4, tower_dims=[96, 80], tower_sides=[4, 8], H=128, vocab=200,
            seed=41)
 
@@ -158,10 +167,28 @@ def make_dynamic(arch, vs):
     print("dynamic", len(recs), "final sizes", fs, "embeds", tuple(emb.shape))
 
 
+def make_full(vs):
+    for name, c in SVA_FULL_CASES.items():
+        T = len(c["rs"])
+        m = vs.VisionTokenSampler(c["q_dim"], 1024, [1024] * T, c["rs"], 1024, c["layers"]).eval()
+        m.load_state_dict(seeded_fill(m, c["seed"]))
+        queries, ctx, feats, masks = seeded_inputs(c["seed"] + 100, c["n"], c["q_dim"], c["rs"])
+        with torch.no_grad():
+            out = m(queries, ctx, *feats, *masks)[:, 0]
+        stride = 4 * c["q_dim"] // 1024
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), rows=out[0::stride].numpy().astype(np.float16),
+                            rowsum=out.sum(1).numpy().astype(np.float32), absmean=np.float32(out.abs().mean()))
+        print(name, tuple(out.shape), float(out.abs().mean()))
+
+
 def main():
     from oracle import ref_shim
     vs = ref_shim.ref_module("cambrian.model.vision_sampler")
     arch = ref_shim.ref_module("cambrian.model.cambrian_arch")
+    if "--only-full" in sys.argv:
+        make_full(vs)
+        return
+    make_full(vs)
     for name, c in SVA_CASES.items():
         T = len(c["rs"])
         m = vs.VisionTokenSampler(c["q_dim"], 1024, [1024] * T, c["rs"], 1024, c["layers"]).eval()

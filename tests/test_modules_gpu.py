@@ -4,8 +4,8 @@ tiny Cambrian model (loss + parameter gradients + greedy generate token ids)."""
 import pytest
 import torch
 
-from helpers import (BF16_TOL, assert_close_bf16, ns, oracle_cfg, rel_err, sd_cpu32, tiny_cambrian_config,
-                     tower_image_sizes)
+from helpers import (FP32_RTOL, ParityCollector, bf, both_modes, ns, oracle_cfg, rel_err, sd_cpu32,
+                     tiny_cambrian_config, tower_image_sizes)
 
 pytestmark = pytest.mark.gpu
 dev = "cuda"
@@ -41,33 +41,39 @@ def test_sva_sampler_matches_oracle(rs, use_mask):
             mk = torch.rand(n, r * r) > 0.3
             mk[mk.sum(1) == 0] = True
             masks.append(mk)
-    bf = lambda t: t.bfloat16().float()
-    # ---- oracle (fp32, CPU, autograd)
-    qo = bf(queries).requires_grad_()
-    fo = [bf(f).requires_grad_() for f in feats]
-    ref = O.sva_sampler(sd, "", qo, bf(ctx), [O.window_rearrange(f, q) for f in fo], masks, depth)
-    dout = torch.randn_like(ref)
-    ref.backward(bf(dout))
+    names = list(sd.keys())
+    dout = torch.randn(n, 1, D)
+
+    def run(sdd, qq, cx, dy, *fm):
+        sdd = {k: v.detach().requires_grad_() for k, v in sdd.items()}
+        qq = qq.detach().requires_grad_()
+        fs = [f.detach().requires_grad_() for f in fm[:T]]
+        out = O.sva_sampler(sdd, "", qq, cx, [O.window_rearrange(f, q) for f in fs], None if masks is None else list(fm[T:]),
+                            depth)
+        return out.detach(), torch.autograd.grad(out, [qq, *fs, *[sdd[k] for k in names]], dy)
+
+    (ref, gref), (eag, geag) = both_modes(run, sd, bf(queries), bf(ctx), bf(dout), *[bf(f) for f in feats], *(masks or []))
     # ---- CUDA, natural layout (fast path)
     qg = queries.to(dev).bfloat16().requires_grad_()
     fg = [f.to(dev).bfloat16().requires_grad_() for f in feats]
     mg = [None] * T if masks is None else [mk.to(dev) for mk in masks]
     out = m(qg, ctx.to(dev).bfloat16(), *fg, *mg, natural_layout=(B, q))
     out.backward(dout.to(dev).bfloat16())
-    assert_close_bf16(out, ref, "sva forward (natural)")
-    assert_close_bf16(qg.grad, qo.grad, "sva dqueries")
+    pc = ParityCollector()
+    tag = f"sva rs={rs}"
+    pc.check(out, ref, eag, f"{tag}: forward (natural)")
+    pc.check(qg.grad, gref[0], geag[0], f"{tag}: dqueries")
     for i in range(T):
-        assert_close_bf16(fg[i].grad, fo[i].grad, f"sva dfeats[{i}]")
-    gref = torch.autograd.grad(O.sva_sampler({k: v.requires_grad_() for k, v in sd.items()}, "", bf(queries), bf(ctx),
-                                             [O.window_rearrange(bf(f), q) for f in feats], masks, depth),
-                               [sd[k] for k in sd], bf(dout))
-    for (k, p), g in zip(m.named_parameters(), gref):
-        assert_close_bf16(p.grad, g, f"sva grad {k}", tol=4e-2, cos=0.995)
+        pc.check(fg[i].grad, gref[1 + i], geag[1 + i], f"{tag}: dfeats[{i}]")
+    params = dict(m.named_parameters())
+    for j, k in enumerate(names):
+        pc.check(params[k].grad, gref[1 + T + j], geag[1 + T + j], f"{tag}: grad {k}")
     # ---- CUDA, reference call convention (window-rearranged latents): same numbers
     m.zero_grad()
     fw = [O.window_rearrange(bf(f), q).to(dev).bfloat16() for f in feats]
     out_w = m(queries.to(dev).bfloat16(), ctx.to(dev).bfloat16(), *fw, *mg)
-    assert_close_bf16(out_w, ref, "sva forward (window-rearranged API)")
+    pc.check(out_w, ref, eag, f"{tag}: forward (window-rearranged API)")
+    pc.done()
     assert rel_err(out_w, out) < 1e-2
 
 
@@ -110,22 +116,19 @@ def test_tower_matches_oracle(kind):
     img = torch.randn(2, 3, R, R)
     c = tower.cfg
     interp = tower._interp_size
+    common = dict(num_hidden_layers=c.get("num_hidden_layers"), patch_size=14,
+                  num_attention_heads=c.get("num_attention_heads"), interp=interp)
+    fn = {"clip": lambda s_, im: O.clip_vit(s_, dict(common, select_layer=-2), im),
+          "dino": lambda s_, im: O.dinov2_vit(s_, common, im),
+          "siglip": lambda s_, im: O.siglip_vit(s_, common, im),
+          "convnext": lambda s_, im: O.convnext_trunk(s_, dict(depths=c["depths"], interp=interp, multi_stage=True), im)}[kind]
     with torch.no_grad():
-        if kind == "clip":
-            ref = O.clip_vit(sd, dict(num_hidden_layers=c["num_hidden_layers"], patch_size=14,
-                                      num_attention_heads=c["num_attention_heads"], select_layer=-2, interp=interp),
-                             img.bfloat16().float())
-        elif kind == "dino":
-            ref = O.dinov2_vit(sd, dict(num_hidden_layers=c["num_hidden_layers"], patch_size=14,
-                                        num_attention_heads=c["num_attention_heads"], interp=interp), img.bfloat16().float())
-        elif kind == "siglip":
-            ref = O.siglip_vit(sd, dict(num_hidden_layers=c["num_hidden_layers"], patch_size=14,
-                                        num_attention_heads=c["num_attention_heads"], interp=interp), img.bfloat16().float())
-        else:
-            ref = O.convnext_trunk(sd, dict(depths=c["depths"], interp=interp, multi_stage=True), img.bfloat16().float())
+        ref, eag = both_modes(fn, sd, bf(img))
         got = tower(img.to(dev).bfloat16())
     assert got.shape == ref.shape, (got.shape, ref.shape)
-    assert_close_bf16(got, ref, f"{kind} tower", tol=4e-2, cos=0.998)
+    pc = ParityCollector()
+    pc.check(got, ref, eag, f"{kind} tower (small)")
+    pc.done()
 
 
 def test_decoder_layer_matches_oracle():
@@ -149,29 +152,36 @@ def test_decoder_layer_matches_oracle():
     kmask[1, 270:] = False
     kmask[0, 40:50] = False
     ocfg = oracle_cfg(cfg)
-    xo = x.bfloat16().float().requires_grad_()
-    cos, sin = O.rope_cos_sin(pos, H // cfg.num_attention_heads, ocfg["rope_theta"])
-    ref = O.llama_layer(sd, "model.layers.0.", xo, cos, sin, kmask, ocfg)
-    dout = torch.randn_like(ref)
+    dout = torch.randn(B, S, H)
     dout[~kmask] = 0  # padded query rows carry no loss
-    ref.backward(dout.bfloat16().float())
+    names = list(sd.keys())
+    hd = H // cfg.num_attention_heads
+
+    def run(sdd, xx, dy, pp, km):
+        sdd = {k: v.detach().requires_grad_() for k, v in sdd.items()}
+        xx = xx.detach().requires_grad_()
+        cos, sin = O.rope_cos_sin(pp, hd, ocfg["rope_theta"])
+        out = O.llama_layer(sdd, "model.layers.0.", xx, cos, sin, km, ocfg)
+        return out.detach(), torch.autograd.grad(out, [xx, *[sdd[k] for k in names]], dy)
+
+    (ref, gref), (eag, geag) = both_modes(run, sd, bf(x), bf(dout), pos, kmask)
     cos_t, sin_t = rope_tables(cfg, torch.device(dev))
+    pc = ParityCollector()
+    valid = kmask.to(dev)
+    params = dict(layer.named_parameters())
     for recompute in (False, True):
         layer.zero_grad()
-        rt = dict(pos=pos.to(dev).reshape(-1).contiguous(), cos=cos_t, sin=sin_t, kmask=kmask.to(dev), hf_cast=False,
+        rt = dict(pos=pos.to(dev).reshape(-1).contiguous(), cos=cos_t, sin=sin_t, kmask=valid, hf_cast=False,
                   recompute=recompute)
         xg = x.to(dev).bfloat16().requires_grad_()
         out = layer(xg, rt)
         out.backward(dout.to(dev).bfloat16())
-        valid = kmask.to(dev)
-        assert_close_bf16(out[valid], ref[kmask], f"decoder layer fwd (recompute={recompute})")
-        assert_close_bf16(xg.grad[valid], xo.grad[kmask], "decoder layer dx", tol=4e-2, cos=0.998)
-        gref = torch.autograd.grad(
-            O.llama_layer({k: v.requires_grad_() for k, v in sd.items()}, "model.layers.0.", x.bfloat16().float(), cos, sin,
-                          kmask, ocfg), [sd[k] for k in sd], dout.bfloat16().float())
-        name2g = dict(zip(sd.keys(), gref))
-        for k, p in layer.named_parameters():
-            assert_close_bf16(p.grad, name2g["model.layers.0." + k], f"decoder grad {k}", tol=5e-2, cos=0.995)
+        tag = f"decoder layer (recompute={recompute})"
+        pc.check(out[valid], ref[valid], eag[valid], f"{tag}: fwd")
+        pc.check(xg.grad[valid], gref[0][valid], geag[0][valid], f"{tag}: dx")
+        for j, k in enumerate(names):
+            pc.check(params[k[len("model.layers.0."):]].grad, gref[1 + j], geag[1 + j], f"{tag}: grad {k}")
+    pc.done()
 
 
 def _build_tiny_model(cfg):
@@ -216,30 +226,32 @@ def _tiny_batch(cfg, B=2, S=96):
     return ids, labels, attn, pos, images, masks
 
 
-def _oracle_tower_feats(model, images):
+TOWER_KINDS = ("siglip", "clip", "dino", "convnext")
+
+
+def _tower_fn(kind, t):
     from oracle import cambrian_oracle as O
+    c = t.cfg
+    common = dict(num_hidden_layers=c.get("num_hidden_layers"), patch_size=14,
+                  num_attention_heads=c.get("num_attention_heads"), interp=t._interp_size)
+    if kind == "siglip":
+        return lambda sd, im: O.siglip_vit(sd, common, im)
+    if kind == "clip":
+        return lambda sd, im: O.clip_vit(sd, dict(common, select_layer=-2), im)
+    if kind == "dino":
+        return lambda sd, im: O.dinov2_vit(sd, common, im)
+    return lambda sd, im: O.convnext_trunk(sd, dict(depths=c["depths"], interp=t._interp_size, multi_stage=True), im)
+
+
+def _oracle_tower_feats(model, images):
+    """fp32 oracle towers on the CPU; features rounded to bf16 (the CUDA towers hand bf16 features to the trainable part)."""
     towers = model.get_model().vision_tower_aux_list
-    bf = lambda t: t.bfloat16().float()
-    feats = []
     with torch.no_grad():
-        for kind, t, img in zip(("siglip", "clip", "dino", "convnext"), towers, images):
-            tsd = sd_cpu32(t.vision_tower)
-            c = t.cfg
-            common = dict(num_hidden_layers=c.get("num_hidden_layers"), patch_size=14,
-                          num_attention_heads=c.get("num_attention_heads"), interp=t._interp_size)
-            if kind == "siglip":
-                f = O.siglip_vit(tsd, common, bf(img))
-            elif kind == "clip":
-                f = O.clip_vit(tsd, dict(common, select_layer=-2), bf(img))
-            elif kind == "dino":
-                f = O.dinov2_vit(tsd, common, bf(img))
-            else:
-                f = O.convnext_trunk(tsd, dict(depths=c["depths"], interp=t._interp_size, multi_stage=True), bf(img))
-            feats.append(bf(f))  # the CUDA towers hand bf16 features to the trainable part
-    return feats
+        return [bf(_tower_fn(kind, t)(sd_cpu32(t.vision_tower), bf(img))) for kind, t, img in zip(TOWER_KINDS, towers, images)]
 
 
 def _oracle_forward(model, cfg, ids, labels, attn, pos, images, masks):
+    """fp32 oracle, CPU (used by __graft_entry__.smoke and the engine tests)."""
     from oracle import cambrian_oracle as O
     sd = sd_cpu32(model)
     feats = _oracle_tower_feats(model, images)
@@ -252,6 +264,37 @@ def _oracle_forward(model, cfg, ids, labels, attn, pos, images, masks):
     return logits, loss, sdg
 
 
+def oracle_full_model_both(model, cfg, ids, labels, attn, pos, images, masks):
+    """The whole hot path (towers -> connector -> splice -> decoder with SVA sites -> loss, + every parameter gradient)
+    through the oracle in fp32 and in eager bf16.  Returns ((logits, loss, {name: grad}), same for eager)."""
+    from oracle import cambrian_oracle as O
+    towers = model.get_model().vision_tower_aux_list
+    sd = sd_cpu32(model)
+    names = list(sd.keys())
+    for i, t in enumerate(towers):
+        sd.update({f"tower{i}." + k: v for k, v in sd_cpu32(t.vision_tower).items()})
+    fns = [_tower_fn(kind, t) for kind, t in zip(TOWER_KINDS, towers)]
+    ocfg = oracle_cfg(cfg)
+
+    def run(s, ii, ll, aa, pp, *im_masks):
+        ims, mks = im_masks[:len(towers)], list(im_masks[len(towers):])
+        with torch.no_grad():
+            feats = []
+            for i, (f, im) in enumerate(zip(fns, ims)):
+                tsd = {k[len(f"tower{i}."):]: v for k, v in s.items() if k.startswith(f"tower{i}.")}
+                o = f(tsd, im)
+                feats.append(o.to(torch.bfloat16).to(o.dtype))     # towers hand bf16 features on (frozen, no grad)
+        s = {k: (v.detach().requires_grad_() if k in names else v) for k, v in s.items()}
+        img, feats_w, ctx_q = O.connector(s, ocfg, feats, mks)
+        emb = O.splice(s, ii, img)
+        hid = O.decoder(s, ocfg, emb, pp, aa, feats_w, mks, ctx_q)
+        logits, loss = O.lm_loss(s, hid, ll)
+        grads = torch.autograd.grad(loss, [s[k] for k in names], allow_unused=True)
+        return logits.detach(), loss.detach(), dict(zip(names, grads))
+
+    return both_modes(run, sd, ids, labels, attn, pos, *[bf(i) for i in images], *masks)
+
+
 @pytest.mark.parametrize("fused_loss", [False, True])
 def test_full_model_loss_and_grads_match_oracle(fused_loss):
     cfg = tiny_cambrian_config()
@@ -259,26 +302,27 @@ def test_full_model_loss_and_grads_match_oracle(fused_loss):
     model = _build_tiny_model(cfg)
     model.train()
     ids, labels, attn, pos, images, masks = _tiny_batch(cfg)
-    ref_logits, ref_loss, sdg = _oracle_forward(model, cfg, ids, labels, attn, pos, images, masks)
-    ref_loss.backward()
+    (ref_logits, ref_loss, gref), (eag_logits, eag_loss, geag) = oracle_full_model_both(
+        model, cfg, ids, labels, attn, pos, images, masks)
     out = model(input_ids=ids.to(dev), labels=labels.to(dev), attention_mask=attn.to(dev), position_ids=pos.to(dev),
                 images=[i.to(dev).bfloat16() for i in images], image_aux_attention_masks_list=[m.to(dev) for m in masks])
     out.loss.backward()
-    assert abs(out.loss.item() - ref_loss.item()) < 2e-2 * abs(ref_loss.item()), (out.loss.item(), ref_loss.item())
+    # loss is an fp32 scalar: north_star's rtol, or the eager path's own deviation when that is larger
+    lim = max(FP32_RTOL * abs(ref_loss.item()), 1.5 * abs(eag_loss.item() - ref_loss.item()))
+    assert abs(out.loss.item() - ref_loss.item()) <= lim, (out.loss.item(), ref_loss.item(), eag_loss.item())
+    pc = ParityCollector()
+    tag = f"tiny model (fused_loss={fused_loss})"
     if not fused_loss:
-        valid = attn[:, :, None].expand_as(ref_logits)
-        assert_close_bf16(out.logits.cpu()[valid], ref_logits[valid], "logits", tol=5e-2, cos=0.995)
-    bad = []
+        valid = attn.to(dev)
+        pc.check(out.logits[valid], ref_logits[valid], eag_logits[valid], f"{tag}: logits")
     for k, p in model.named_parameters():
-        g = sdg[k].grad
+        g = gref[k]
         if g is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         assert p.grad is not None, f"missing grad for {k}"
-        e = rel_err(p.grad, g)
-        if e > 8e-2:
-            bad.append((k, e))
-    assert not bad, f"gradient mismatches: {bad[:10]}"
+        pc.check(p.grad, g, geag[k], f"{tag}: grad {k}")
+    pc.done()
 
 
 def test_engine_overlapped_optimizer_matches_serial():
@@ -315,9 +359,8 @@ def test_engine_overlapped_optimizer_matches_serial():
     assert results[2][2][0] == results[1][2][0]
 
 
-def test_engine_step_and_greedy_generate():
-    """TrainEngine (flat buffers, main_grad accumulation, fused AdamW) must reproduce plain-autograd gradients, and
-    greedy generation must be token-exact against the oracle's greedy decode on the same weights."""
+def test_engine_step_reproduces_autograd_gradients():
+    """TrainEngine (flat buffers, main_grad accumulation, fused AdamW) must reproduce plain-autograd gradients."""
     from cambrian_b200.engine import TrainEngine
     from oracle import cambrian_oracle as O
     cfg = tiny_cambrian_config()
@@ -343,32 +386,7 @@ def test_engine_step_and_greedy_generate():
     eng.step()
     assert float((eng.flat_p.float() - before.float()).abs().max()) > 0
     assert torch.isfinite(eng.master).all()
-    # ---- greedy decode parity (eval numerics: HF rmsnorm cast order)
-    model.eval()
-    S0 = 40
-    gen_ids = ids[:1, :S0].clone()
-    new = model.generate(gen_ids.to(dev), images=[i[:1].to(dev).bfloat16() for i in images], image_sizes=[(56, 56)],
-                         max_new_tokens=4, do_sample=False)
-    sd = sd_cpu32(model)
-    with torch.no_grad():
-        cur_ids, cur_pos = gen_ids.clone(), torch.arange(S0)[None]
-        toks = []
-        ocfg = oracle_cfg(cfg)
-        bf = lambda t: t.bfloat16().float()
-        towers = model.get_model().vision_tower_aux_list
-        feats = [bf(t(i[:1].to(dev).bfloat16()).float().cpu()) for t, i in zip(towers, images)]
-        img, feats_w, ctx_q = O.connector(sd, ocfg, feats, None)
-        emb = O.splice(sd, cur_ids, img)
-        for _ in range(4):
-            hid = O.decoder(sd, ocfg, emb, torch.arange(emb.shape[1])[None], None, feats_w, None, ctx_q)
-            logits, _ = O.lm_loss(sd, hid[:, -1:], None)
-            nxt = int(logits[0, -1].argmax())
-            toks.append(nxt)
-            emb = torch.cat([emb, sd["model.embed_tokens.weight"][nxt][None, None]], 1)
-    assert new.shape == (1, 4)
-    # bf16 vs fp32 argmax can legitimately differ on near-ties; require the first token and >= 3 of 4 to agree
-    got = new[0].tolist()
-    assert got[0] == toks[0] and sum(int(a == b) for a, b in zip(got, toks)) >= 3, (got, toks)
+    # greedy decode parity: tests/test_parity_gpu.py::test_greedy_generate_token_exact_32_tokens
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -401,9 +419,14 @@ def test_dynamic_branch_logits_match_oracle():
         assert fs == [(2, 4), (4, 2)]
         hid = O.decoder_dynamic(sd, ocfg, emb, pos, am, ff, mf, ctx, fs)
         ref_logits, _ = O.lm_loss(sd, hid, None)
+        sdb = O.eager_bf16(sd)
+        feats_b = [f.bfloat16() for f in feats]
+        emb_b, _, _, _, ff_b, mf_b, _, ctx_b = O.prepare_dynamic(sdb, ocfg, feats_b, ids, attn, None, sizes)
+        eag_logits, _ = O.lm_loss(sdb, O.decoder_dynamic(sdb, ocfg, emb_b, pos, am, ff_b, mf_b, ctx_b, fs), None)
     assert out.logits.shape == ref_logits.shape
-    valid = am[:, :, None].expand_as(ref_logits)
-    assert_close_bf16(out.logits.cpu()[valid], ref_logits[valid], "dynamic-branch logits", tol=5e-2, cos=0.995)
+    pc = ParityCollector()
+    pc.check(out.logits.cpu()[am], ref_logits[am], eag_logits[am], "dynamic-branch logits")
+    pc.done()
 
 
 def test_dynamic_branch_equals_static_branch_for_square_images():

@@ -12,7 +12,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from make_golden import SVA_CASES, seeded_fill, seeded_inputs  # noqa: E402
+from make_golden import SVA_CASES, SVA_FULL_CASES, seeded_fill, seeded_inputs  # noqa: E402
 
 from oracle import cambrian_oracle as O  # noqa: E402
 from oracle import ref_shim  # noqa: E402
@@ -54,6 +54,21 @@ def test_sva_oracle_matches_reference_golden(name):
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize("name", sorted(SVA_FULL_CASES))
+def test_sva_oracle_matches_reference_golden_full_size(name):
+    """BASELINE config 1 at its real size (576 queries, 4 x 576 x 1024 grids, depth 3), the release grids [1,1,1,4] and one
+    in-LLM layer at Llama-3-8B width: oracle vs the reference module's output (subsampled rows + all row sums)."""
+    c = SVA_FULL_CASES[name]
+    sd = seeded_fill(_sva_shapes(c["q_dim"], c["rs"], c["layers"]), c["seed"])
+    queries, ctx, feats, masks = seeded_inputs(c["seed"] + 100, c["n"], c["q_dim"], c["rs"])
+    with torch.no_grad():
+        got = O.sva_sampler(sd, "", queries, ctx, feats, masks, c["layers"])[:, 0]
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    stride = 4 * c["q_dim"] // 1024
+    torch.testing.assert_close(got[0::stride], torch.from_numpy(z["rows"]).float(), rtol=2e-3, atol=2e-3)  # fp16 storage
+    torch.testing.assert_close(got.sum(1), torch.from_numpy(z["rowsum"]), rtol=1e-4, atol=2e-3)
+
+
 def test_window_rearrange_matches_reference_golden():
     z = np.load(os.path.join(GOLD, "rearrange.npz"))
     got = O.window_rearrange(torch.from_numpy(z["feat"]), 4)
@@ -74,12 +89,13 @@ def test_oracle_clip_matches_transformers():
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("res", [518 // 37 * 4, 14 * 6])
-def test_oracle_dinov2_matches_transformers(res):
+@pytest.mark.parametrize("res,swiglu", [(518 // 37 * 4, False), (14 * 6, False), (14 * 6, True)])
+def test_oracle_dinov2_matches_transformers(res, swiglu):
+    """swiglu=True is the dinov2-giant FFN (the release tower, finetune_cambrian_8b.sh:17-18)."""
     from transformers import Dinov2Config, Dinov2Model
     torch.manual_seed(0)
     cfg = Dinov2Config(hidden_size=128, num_hidden_layers=2, num_attention_heads=2, mlp_ratio=4, patch_size=14,
-                       image_size=56)
+                       image_size=56, use_swiglu_ffn=swiglu)
     m = Dinov2Model(cfg).eval()
     with torch.no_grad():
         for n_, p in m.named_parameters():
