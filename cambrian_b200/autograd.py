@@ -24,9 +24,32 @@ def _notify(param):
         n()
 
 
-def wgrad(param: torch.Tensor, dy2d: torch.Tensor, x2d: torch.Tensor, out_view=None):
+def _await(*params):
+    """Before a block's first kernel reads `params`: make the current stream wait for optimizer updates of their buckets
+    that the TrainEngine still has in flight on its side stream (engine.await_bucket; a no-op dictionary miss otherwise).
+    Accepts nn.Parameters and the fused-weight holders of cambrian_llama (`_params`)."""
+    for p in params:
+        if p is None:
+            continue
+        eng = getattr(p, "_cb_engine", None)
+        if eng is not None:
+            eng.await_bucket(p._cb_bucket)
+        else:
+            for q in getattr(p, "_params", ()):
+                eng = getattr(q, "_cb_engine", None)
+                if eng is not None:
+                    eng.await_bucket(q._cb_bucket)
+
+
+def _frozen(param) -> bool:
+    return not getattr(param, "requires_grad", True)
+
+
+def wgrad(param: torch.Tensor, dy2d: torch.Tensor, x2d: torch.Tensor, out_view=None, notify: bool = True):
     """dW[N_out, K_in] = dy2d[rows, N_out]^T @ x2d[rows, K_in].  `out_view` selects a column slice of the gradient
-    (used for proj_in's two halves)."""
+    (used for proj_in's two halves).  Frozen parameters (stage-1 connector pre-training freezes the LLM) cost nothing."""
+    if _frozen(param):
+        return None
     mg = getattr(param, "main_grad", None)
     if mg is not None:
         tgt = mg if out_view is None else out_view(mg)
@@ -36,13 +59,16 @@ def wgrad(param: torch.Tensor, dy2d: torch.Tensor, x2d: torch.Tensor, out_view=N
         ops.gemm(dy2d, x2d, a_mn=True, b_mn=True, out=tgt, accumulate=not first)
         if fresh is not None:
             fresh.add(key)
-        _notify(param)
+        if notify:
+            _notify(param)
         return None
     return ops.gemm(dy2d, x2d, a_mn=True, b_mn=True)
 
 
 def vgrad(param: torch.Tensor, g: torch.Tensor):
     """Gradient of a vector/small parameter computed by a reduction kernel (bf16)."""
+    if _frozen(param):
+        return None
     mg = getattr(param, "main_grad", None)
     if mg is not None:
         fresh = getattr(param, "_cb_fresh", None)
@@ -67,6 +93,7 @@ def _merge_wgrad(parts):
 class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
+        _await(weight, bias)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         ctx.params = (weight, bias)
@@ -102,6 +129,7 @@ class ActFn(torch.autograd.Function):
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps):
+        _await(weight, bias)
         y, mean, rstd = ops.layernorm_fwd(x, weight, bias, eps, save_stats=True)
         ctx.save_for_backward(x, weight, mean, rstd)
         ctx.params = (weight, bias)
@@ -117,6 +145,7 @@ class LayerNormFn(torch.autograd.Function):
 class RMSNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, eps, hf_cast):
+        _await(weight)
         y, rstd = ops.rmsnorm_fwd(x, weight, eps, hf_cast, save_stats=True)
         ctx.save_for_backward(x, weight, rstd)
         ctx.param = weight
@@ -157,6 +186,7 @@ class SVALayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, queries, ctxf, *tensors):
         T, rs = meta["T"], meta["rs"]
+        _await(*meta["params"])
         feats = [t.reshape(-1, t.shape[-1]) for t in tensors[:T]]
         P = dict(zip(meta["names"], tensors[T:]))
         N, D = queries.shape
@@ -324,6 +354,7 @@ class DecoderLayerFn(torch.autograd.Function):
         # q_w/k_w/v_w and gate_w/up_w are the HF-named leaf parameters (for autograd bookkeeping); the GEMMs use the
         # fused views meta["qkv_w"] / meta["gu_w"] over the same storage (CBLlamaDecoderLayer._fused()).
         keep = not meta["recompute"]
+        _await(*meta["params"])
         qkv_w, gu_w = meta["qkv_w"], meta["gu_w"]
         out, saved = DecoderLayerFn._forward(meta, x, ln1, qkv_w, o_w, ln2, gu_w, down_w, keep)
         ctx.meta = meta
@@ -399,6 +430,7 @@ class EmbedSpliceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, embed_w, img, newline):
         ids, img_start, q_side = meta["ids"], meta["img_start"], meta["q_side"]
+        _await(*meta["params"])
         ctx.meta = meta
         ctx.has_img = img is not None
         ctx.vshape = embed_w.shape
@@ -447,6 +479,8 @@ class LMHeadLossFn(torch.autograd.Function):
         n_valid = meta["n_valid"]  # python int (known on the host from the collator) — no device sync
         train = meta["train"]
         p_w = meta["params"][0]
+        _await(p_w)
+        need_dw = train and not _frozen(p_w)
         # Rows whose shifted label is ignore_index contribute neither loss nor gradient.  When the collator hands over
         # the row ranges that can hold a valid label (host ints, `label_ranges`), only those rows are pushed through the
         # vocabulary GEMMs: they are packed into one dense buffer (device-to-device copies), dhidden of all other rows
@@ -469,10 +503,13 @@ class LMHeadLossFn(torch.autograd.Function):
         loss_rows = torch.empty(rows, dtype=torch.float32, device=dev)
         acc = torch.zeros(2, dtype=torch.float32, device=dev)
         dh = torch.empty_like(h2) if train else None
-        gscale = 1.0 / max(n_valid, 1)
+        # `loss_scale` (TrainEngine: e.g. 1 / gradient_accumulation_steps) is folded into the gradients formed here; the
+        # returned loss value is the unscaled mean.  The gradients are final when forward returns: backward() only hands
+        # out dhidden, so `(loss * c).backward()` with c != 1 is NOT supported on this path (use loss_scale).
+        gscale = float(meta.get("loss_scale", 1.0)) / max(n_valid, 1)
         logits = torch.empty((min(chunk, rows), V), dtype=torch.bfloat16, device=dev)
         dw_local = None
-        if train and getattr(p_w, "main_grad", None) is None:
+        if need_dw and getattr(p_w, "main_grad", None) is None:
             dw_local = torch.empty_like(weight)
         for r0 in range(0, rows, chunk):
             r1 = min(rows, r0 + chunk)
@@ -481,10 +518,14 @@ class LMHeadLossFn(torch.autograd.Function):
             ops.cross_entropy(lg, labels[r0:r1], loss_rows[r0:r1], acc, gscale, train)
             if train:
                 ops.gemm(lg, weight, b_mn=True, out=dh[r0:r1])
-                if dw_local is None:
-                    wgrad(p_w, lg, h2[r0:r1])
+                if not need_dw:
+                    pass
+                elif dw_local is None:
+                    wgrad(p_w, lg, h2[r0:r1], notify=False)
                 else:
                     ops.gemm(lg, h2[r0:r1], a_mn=True, b_mn=True, out=dw_local, accumulate=r0 > 0)
+        if need_dw and dw_local is None:
+            _notify(p_w)      # ONE contribution per step however many chunks ran: the count must not depend on the data
         if dh_full is not None:
             o = 0
             for a, b in ranges:
@@ -496,15 +537,16 @@ class LMHeadLossFn(torch.autograd.Function):
         ctx.has_dw = dw_local is not None
         if train:
             ctx.save_for_backward(dh, *([dw_local] if dw_local is not None else []))
-        loss = acc[0] * gscale
+        loss = acc[0] / max(n_valid, 1)
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        # dloss is 1.0 for a plain loss.backward(); a scaled loss would need one more scaling kernel
         dh = ctx.saved_tensors[0]
-        dw = ctx.saved_tensors[1] if ctx.has_dw else None
-        return None, dh.view(ctx.hshape), dw
+        if ctx.has_dw:      # plain-autograd path (no TrainEngine): honour an upstream scale, e.g. (loss / accum).backward()
+            return None, (dh * dloss.to(dh.dtype)).view(ctx.hshape), ctx.saved_tensors[1] * dloss.to(dh.dtype)
+        # TrainEngine path: dW already sits in main_grad with `loss_scale` folded in (see forward); dloss must be 1
+        return None, dh.view(ctx.hshape), None
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -82,7 +82,9 @@ int f32_to_bf16_launch(const float*, void*, long long, int, long long, float, cu
 int cross_entropy_launch(void*, const long long*, float*, float*, long long, long long, long long, float, int,
                          long long, cudaStream_t);
 int adamw_launch(float*, float*, float*, const void*, void*, long long, float, float, float, float, float, int, float,
-                 cudaStream_t);
+                 const float*, int, cudaStream_t);
+int sumsq_launch(const void*, long long, float*, float*, long long, int, cudaStream_t);
+int clip_coef_launch(float*, float, float, float*, cudaStream_t);
 int span_gather_launch(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int span_scatter_launch(void*, const void*, int, int, int, int, int, int, cudaStream_t);
 int gemm_swiglu_bf16(const void*, const void*, void*, void*, int, int, int, long long, long long, long long, long long,
@@ -278,7 +280,20 @@ int cb_preprocess_image(const uint8_t* img, int H, int W, int R, const int32_t* 
 }
 int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int step, float grad_scale, void* stream) {
-  return cb::adamw_launch(p, m, v, g, p16, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, ST(stream));
+  return cb::adamw_launch(p, m, v, g, p16, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, nullptr, 0, ST(stream));
+}
+int cb_adamw_ex(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, int step, float grad_scale, const float* clip_coef, int background,
+                void* stream) {
+  return cb::adamw_launch(p, m, v, g, p16, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, clip_coef, background,
+                          ST(stream));
+}
+int cb_sumsq_bf16(const void* g, int64_t n, float* acc, float* workspace, int64_t workspace_floats, int background,
+                  void* stream) {
+  return cb::sumsq_launch(g, n, acc, workspace, workspace_floats, background, ST(stream));
+}
+int cb_clip_coef(float* sumsq, float max_norm, float inv_world, float* coef, void* stream) {
+  return cb::clip_coef_launch(sumsq, max_norm, inv_world, coef, ST(stream));
 }
 
 }  // extern "C"

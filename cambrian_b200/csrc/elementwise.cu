@@ -695,11 +695,19 @@ __global__ void loss_reduce_kernel(const float* __restrict__ loss_rows, const lo
 // -------------------------------------------------------------------------------------- AdamW
 // fp32 master weights + fp32 moments, bf16 gradients in, bf16 compute copy out (torch.optim.AdamW semantics,
 // decoupled weight decay; the reference trains with HF Trainer's AdamW: cambrian_trainer.py:242-381).
+// `coef` (optional, device): gradient scale computed on the device by clip_coef_kernel (1/world x clip factor) — the
+// clipped update needs no host round trip.  `grad_scale` is used when coef is null.
+template <int UNROLL>
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                              const bf16* __restrict__ g, bf16* __restrict__ p16, long long n, float lr, float b1,
-                             float b2, float eps, float wd, float bc1, float bc2, float grad_scale) {
+                             float b2, float eps, float wd, float bc1, float bc2, float grad_scale,
+                             const float* __restrict__ coef) {
   const long long nvec = n >> 3;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+  const float gs = coef ? __ldg(coef) : grad_scale;
+  const float inv_sqrt_bc2 = rsqrtf(bc2), step_size = lr / bc1, decay = 1.f - lr * wd;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll UNROLL
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += stride) {
     float gf[8];
     unpack8(ldg_nc(reinterpret_cast<const uint4*>(g) + i), gf);
     float4* pp = reinterpret_cast<float4*>(p) + 2 * i;
@@ -711,18 +719,56 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ m, float
     *reinterpret_cast<float4*>(vf) = vp[0]; *reinterpret_cast<float4*>(vf + 4) = vp[1];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float gg = gf[e] * grad_scale;
-      pf[e] *= (1.f - lr * wd);
+      const float gg = gf[e] * gs;
+      pf[e] *= decay;
       mf[e] = b1 * mf[e] + (1.f - b1) * gg;
       vf[e] = b2 * vf[e] + (1.f - b2) * gg * gg;
-      const float denom = sqrtf(vf[e]) / sqrtf(bc2) + eps;
-      pf[e] -= (lr / bc1) * (mf[e] / denom);
+      const float denom = sqrtf(vf[e]) * inv_sqrt_bc2 + eps;
+      pf[e] -= step_size * (mf[e] / denom);
     }
     pp[0] = *reinterpret_cast<float4*>(pf); pp[1] = *reinterpret_cast<float4*>(pf + 4);
     mp[0] = *reinterpret_cast<float4*>(mf); mp[1] = *reinterpret_cast<float4*>(mf + 4);
     vp[0] = *reinterpret_cast<float4*>(vf); vp[1] = *reinterpret_cast<float4*>(vf + 4);
     reinterpret_cast<uint4*>(p16)[i] = pack8(pf);
   }
+}
+
+// ---------------------------------------------------------------------------- gradient clipping
+// Sum of squares of a bf16 gradient range, deterministic: per-block partials in `ws`, then one block adds them to *acc in
+// a fixed order (torch.nn.utils.clip_grad_norm_ as HF Trainer calls it with max_grad_norm = 1.0 in every reference script).
+__global__ void sumsq_partial_kernel(const uint4* __restrict__ g, long long nvec, float* __restrict__ ws) {
+  float s = 0.f;
+#pragma unroll 8
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(ldg_nc(g + i), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s = fmaf(f[e], f[e], s);
+  }
+  __shared__ float red[32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+    ws[blockIdx.x] = t;
+  }
+}
+__global__ void sumsq_final_kernel(const float* __restrict__ ws, int nblocks, float* __restrict__ acc) {
+  // one warp, fixed order: lane l sums ws[l], ws[l + 32], ... then a shuffle tree
+  float t = 0.f;
+  for (int i = threadIdx.x; i < nblocks; i += 32) t += ws[i];
+  t = warp_sum(t);
+  if (threadIdx.x == 0) acc[0] += t;
+}
+// coef[0] = inv_world * min(1, max_norm / (norm + 1e-6)),  coef[1] = norm  with norm = sqrt(sumsq) * inv_world (the L2 norm
+// of the rank-averaged gradient);  sumsq is reset for the next step.
+__global__ void clip_coef_kernel(float* __restrict__ sumsq, float max_norm, float inv_world, float* __restrict__ coef) {
+  const float norm = sqrtf(sumsq[0]) * inv_world;
+  coef[0] = inv_world * fminf(1.f, max_norm / (norm + 1e-6f));
+  coef[1] = norm;
+  sumsq[0] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -925,14 +971,45 @@ int cross_entropy_launch(void* logits, const long long* labels, float* loss_rows
   }
   return CB_OK;
 }
+// background != 0: ONE 128-thread block per SM (72 registers x 4 warps = 9.2 K of the 11.8 K registers a resident GEMM CTA
+// — 320 threads x 168 registers, ~200 KB smem — leaves free; no shared memory) so the grid fits NEXT TO a persistent GEMM
+// CTA on every SM: the HBM-bound update then runs underneath tensor-core-bound work instead of taking all 2048 thread
+// slots of each SM and serialising with it (r01: the GEMMs launched behind an 8-blocks/SM AdamW grid ran at ~1000 instead
+// of ~1480 TFLOP/s because their CTAs had to wait).  4 independent 112-byte load groups per thread keep ~57 KB per SM in
+// flight, enough for a few TB/s; it only has to finish under the pass it hides in.
 int adamw_launch(float* p, float* m, float* v, const void* g, void* p16, long long n, float lr, float b1, float b2,
-                 float eps, float wd, int step, float grad_scale, cudaStream_t st) {
+                 float eps, float wd, int step, float grad_scale, const float* clip_coef, int background,
+                 cudaStream_t st) {
   VEC_CHECK(n, "adamw");
   CB_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
+  if (n == 0) return CB_OK;
   const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
-  adamw_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>(p, m, v, (const bf16*)g, (bf16*)p16, n, lr, b1, b2, eps, wd, bc1, bc2,
-                                                    grad_scale);
+  if (background)
+    adamw_kernel<4><<<grid_for(n / 8, 128, 1), 128, 0, st>>>(p, m, v, (const bf16*)g, (bf16*)p16, n, lr, b1, b2, eps, wd,
+                                                            bc1, bc2, grad_scale, clip_coef);
+  else
+    adamw_kernel<1><<<grid_for(n / 8, 256), 256, 0, st>>>(p, m, v, (const bf16*)g, (bf16*)p16, n, lr, b1, b2, eps, wd, bc1,
+                                                         bc2, grad_scale, clip_coef);
   CB_CUDA_LAUNCH_CHECK("adamw");
+  return CB_OK;
+}
+int sumsq_launch(const void* g, long long n, float* acc, float* ws, long long ws_floats, int background, cudaStream_t st) {
+  VEC_CHECK(n, "sumsq");
+  CB_CHECK_ARG(acc && ws, "sumsq: null accumulator / workspace");
+  if (n == 0) return CB_OK;
+  const int threads = background ? 128 : 256;
+  const unsigned grid = grid_for(n / 8, threads, background ? 1 : 8);
+  CB_CHECK_ARG((long long)grid <= ws_floats, "sumsq: workspace too small (%lld < %u floats)", ws_floats, grid);
+  sumsq_partial_kernel<<<grid, threads, 0, st>>>((const uint4*)g, n / 8, ws);
+  CB_CUDA_LAUNCH_CHECK("sumsq_partial");
+  sumsq_final_kernel<<<1, 32, 0, st>>>(ws, (int)grid, acc);
+  CB_CUDA_LAUNCH_CHECK("sumsq_final");
+  return CB_OK;
+}
+int clip_coef_launch(float* sumsq, float max_norm, float inv_world, float* coef, cudaStream_t st) {
+  CB_CHECK_ARG(sumsq && coef && max_norm > 0.f && inv_world > 0.f, "clip_coef: bad arguments");
+  clip_coef_kernel<<<1, 1, 0, st>>>(sumsq, max_norm, inv_world, coef);
+  CB_CUDA_LAUNCH_CHECK("clip_coef");
   return CB_OK;
 }
 

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..autograd import EmbedSpliceFn, ExpandRowsFn, MeanTokensFn
+from ..autograd import EmbedSpliceFn, ExpandRowsFn, MeanTokensFn, _await
 from .multimodal_encoder.builder import build_vision_tower_aux_list
 from .multimodal_projector.builder import CBGELU, CBLayerNorm, CBLinear, build_vision_projector
 from .vision_sampler import VisionTokenSampler
@@ -214,12 +214,13 @@ class CambrianMetaForCausalLM(ABC):
         cfg = model.config
         if torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters()):
             raise NotImplementedError("the dynamic-shape (non-square image) branch is inference-only: run under torch.no_grad()")
+        sync = getattr(self, "_cb_param_sync", None)
+        if sync is not None:
+            sync()
         bs = images[0].shape[0]
         q_num = cfg.image_token_len
         fh = fw = int(q_num ** 0.5)
         feats = self.encode_images(images)
-        if getattr(self, "_cb_param_sync", None) is not None:
-            self._cb_param_sync()
         feats_final = masks_final = ctx_final = None
         if cfg.mm_projector_type == "sva":
             aux = [getattr(model, f"mm_projector_aux_{i}")(f.to(torch.bfloat16)) for i, f in enumerate(feats)]
@@ -228,6 +229,7 @@ class CambrianMetaForCausalLM(ABC):
             for g, query_num in enumerate(cfg.query_num_list):
                 qs = int(query_num ** 0.5)
                 n = bs * query_num
+                _await(model.vision_query)
                 queries = ExpandRowsFn.apply(model.vision_query[g:g + 1].to(torch.bfloat16), n)
                 ctx_g = ExpandRowsFn.apply(ctx, query_num)
                 f_i, m_i = self.rearrange_vision_tower_features_inference(aux, qs, image_sizes)     # :389
@@ -319,8 +321,6 @@ class CambrianMetaForCausalLM(ABC):
         model = self.get_model()
         towers = model.get_vision_tower_aux_list()
         if towers is None or images is None or input_ids.shape[1] == 1:                          # :345-346
-            if getattr(self, "_cb_param_sync", None) is not None:
-                self._cb_param_sync()
             return input_ids, position_ids, attention_mask, past_key_values, None, labels, None, None, None, None
         cfg = model.config
         bs = images[0].shape[0]
@@ -357,9 +357,8 @@ class CambrianMetaForCausalLM(ABC):
         img_start = torch.tensor(starts, dtype=torch.int32).to(input_ids.device, non_blocking=True)
 
         feats = self.encode_images(images)                                                      # :366
-        sync = getattr(self, "_cb_param_sync", None)
-        if sync is not None:
-            sync()            # TrainEngine: optimizer tail of the previous step overlapped the (frozen) towers above
+        # (TrainEngine: the optimizer of the previous step may still be running on its side stream under the frozen towers
+        #  above; every trainable block below waits for exactly its own bucket — autograd._await)
         feats_final = masks_final = ctx_final = None
         if cfg.mm_projector_type == "sva":
             aux = [getattr(model, f"mm_projector_aux_{i}")(f.to(torch.bfloat16)) for i, f in enumerate(feats)]   # :372-379
@@ -369,6 +368,7 @@ class CambrianMetaForCausalLM(ABC):
             for g, query_num in enumerate(cfg.query_num_list):
                 qs = int(query_num ** 0.5)
                 n = bs * query_num
+                _await(model.vision_query)
                 queries = ExpandRowsFn.apply(model.vision_query[g:g + 1].to(torch.bfloat16), n)      # :383
                 ctx_g = ExpandRowsFn.apply(ctx, query_num)                                           # :384
                 masks = _masks_for(image_aux_attention_masks_list, aux, qs, n)

@@ -370,7 +370,7 @@ class _CELossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dloss):
-        return ctx.saved_tensors[0], None, None
+        return ctx.saved_tensors[0] * dloss.to(ctx.saved_tensors[0].dtype), None, None
 
 
 class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM):
@@ -408,8 +408,6 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
         the flattened [B*S] positions outside of which every SHIFTED label is ignore_index (train/collator.py:
         valid_label_ranges) — the fused loss then skips the vocabulary GEMMs of rows that cannot contribute."""
         feats = masks = final_size = ctx_feat = None
-        if inputs_embeds is not None and getattr(self, "_cb_param_sync", None) is not None:
-            self._cb_param_sync()
         if inputs_embeds is None:
             (input_ids, position_ids, attention_mask, past_key_values, inputs_embeds, labels, feats, masks, final_size,
              ctx_feat) = self.prepare_inputs_labels_for_multimodal(
@@ -432,9 +430,12 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
             if num_valid_labels is None:
                 num_valid_labels = int(((shift != IGNORE_INDEX) & (shift >= 0) & (shift < self.vocab_size)).sum())
         if labels is not None and fused:
-            meta = dict(shift_labels=shift, n_valid=num_valid_labels, train=torch.is_grad_enabled(),
+            # gradients are formed inside the fused forward: only when something will consume them (training mode, or no
+            # TrainEngine buffers to write into) — an eval pass with labels under grad mode must not touch main_grad
+            train = torch.is_grad_enabled() and (self.training or getattr(self.lm_head.weight, "main_grad", None) is None)
+            meta = dict(shift_labels=shift, n_valid=num_valid_labels, train=train,
                         params=(self.lm_head.weight,), chunk=getattr(self.config, "lm_loss_chunk", 4096),
-                        label_ranges=label_ranges)
+                        label_ranges=label_ranges, loss_scale=getattr(self, "_cb_loss_scale", 1.0))
             loss = LMHeadLossFn.apply(meta, hidden, self.lm_head.weight)
         else:
             logits_bf16 = LinearFn.apply(hidden, self.lm_head.weight, None)                     # :408
@@ -454,6 +455,9 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
         temperature=0 (greedy).  Returns the newly generated ids [B, T] like HF generate does for `inputs_embeds`."""
         if "inputs_embeds" in kwargs:
             raise NotImplementedError("`inputs_embeds` is not supported")                       # :447-448
+        sync = getattr(self, "_cb_param_sync", None)
+        if sync is not None:
+            sync()      # a TrainEngine with deferred parameter sync: inference kernels read parameters directly
         if kwargs.get("do_sample", False) and kwargs.get("temperature", 1.0) not in (0, 0.0):
             raise NotImplementedError("only greedy decoding is implemented")
         max_new = int(kwargs.get("max_new_tokens", 32))

@@ -426,9 +426,25 @@ def cross_entropy(logits, labels, loss_rows, loss_acc, grad_scale: float, write_
                                        float(grad_scale), int(write_grad), ignore_index, stream()), "cb_cross_entropy")
 
 
-def adamw(p32, m, v, g16, p16, lr, beta1, beta2, eps, wd, step: int, grad_scale: float = 1.0):
-    check(_lib.load().cb_adamw(ptr(p32), ptr(m), ptr(v), ptr(g16), ptr(p16), p32.numel(), float(lr), float(beta1),
-                               float(beta2), float(eps), float(wd), int(step), float(grad_scale), stream()), "cb_adamw")
+def adamw(p32, m, v, g16, p16, lr, beta1, beta2, eps, wd, step: int, grad_scale: float = 1.0, clip_coef=None,
+          background: bool = False):
+    """clip_coef: optional fp32 DEVICE tensor whose element 0 replaces grad_scale (written by `clip_coef`);
+    background: one small block per SM so the update co-resides with persistent GEMM CTAs."""
+    check(_lib.load().cb_adamw_ex(ptr(p32), ptr(m), ptr(v), ptr(g16), ptr(p16), p32.numel(), float(lr), float(beta1),
+                                  float(beta2), float(eps), float(wd), int(step), float(grad_scale), ptr(clip_coef),
+                                  int(background), stream()), "cb_adamw_ex")
+
+
+def sumsq_accumulate(g16, acc, ws, background: bool = True):
+    """acc[0] += sum(g16^2) (deterministic); g16 bf16 contiguous with numel % 8 == 0; ws fp32 scratch (>= 4096)."""
+    _require_cuda_bf16(g16)
+    check(_lib.load().cb_sumsq_bf16(ptr(g16), g16.numel(), ptr(acc), ptr(ws), ws.numel(), int(background), stream()),
+          "cb_sumsq_bf16")
+
+
+def clip_coef(sumsq, max_norm: float, inv_world: float, coef):
+    """coef[0] = inv_world * min(1, max_norm / (norm + 1e-6)), coef[1] = norm of the averaged gradient; resets sumsq."""
+    check(_lib.load().cb_clip_coef(ptr(sumsq), float(max_norm), float(inv_world), ptr(coef), stream()), "cb_clip_coef")
 
 
 def span_gather(hidden, start: int, q_side: int):

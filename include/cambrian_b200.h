@@ -199,6 +199,19 @@ int cb_preprocess_image(const uint8_t* img, int H, int W, int R, const int32_t* 
 /* AdamW on fp32 master weights / moments with bf16 gradients, writing the bf16 compute copy */
 int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* cb_adamw with (a) the gradient scale read from DEVICE memory (clip_coef[0], written by cb_clip_coef; null = use
+ * grad_scale) so a clipped step needs no host sync, and (b) a background launch shape (one small block per SM) that
+ * co-resides with a persistent GEMM CTA on every SM.  Replaces HF Trainer's clip_grad_norm_ + AdamW.step
+ * (cambrian_trainer.py:242-381; transformers Trainer max_grad_norm default 1.0). */
+int cb_adamw_ex(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
+                float eps, float weight_decay, int step, float grad_scale, const float* clip_coef, int background,
+                void* stream);
+/* acc[0] += sum of squares of n bf16 values (deterministic two-stage reduction; workspace >= grid floats, 4096 suffices) */
+int cb_sumsq_bf16(const void* g, int64_t n, float* acc, float* workspace, int64_t workspace_floats, int background,
+                  void* stream);
+/* coef[0] = inv_world * min(1, max_norm / (sqrt(sumsq[0]) * inv_world + 1e-6)); coef[1] = that norm; sumsq[0] = 0
+ * (torch.nn.utils.clip_grad_norm_ on the rank-averaged gradient, all on the device) */
+int cb_clip_coef(float* sumsq, float max_norm, float inv_world, float* coef, void* stream);
 
 #ifdef __cplusplus
 }

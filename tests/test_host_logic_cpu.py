@@ -179,8 +179,9 @@ def _zero2_worker(rank, world, port, q):
     model = torch.nn.Sequential(torch.nn.Linear(16, 24, bias=True), torch.nn.Linear(24, 9, bias=False)).bfloat16()
     eng = E.TrainEngine(model, zero_stage=2)
     assert eng.total == eng.shard * world and eng.master.numel() == eng.shard   # optimizer state is sharded
+    assert all((e - s) % (8 * world) == 0 for s, e, _ in eng.buckets)           # every rank owns an aligned piece of each bucket
     # stand-in for the CUDA AdamW kernel (not available on CPU): plain SGD on the fp32 master slice
-    def sgd(master, m, v, g, p16):
+    def sgd(master, m, v, g, p16, lr, wd, step, coef):
         master.sub_(0.5 * g.float() / world)
         p16.copy_(master.to(torch.bfloat16))
     eng._adamw = sgd
