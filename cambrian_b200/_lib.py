@@ -53,6 +53,7 @@ SIGNATURES = {
     "cb_pos_grad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "cb_f32_to_bf16": (_i, [_vp, _vp, _i64, _i, _i64, _f, _vp]),
     "cb_cross_entropy": (_i, [_vp] * 4 + [_i64, _i64, _i64, _f, _i, _i64, _vp]),
+    "cb_cross_entropy_ex": (_i, [_vp] * 4 + [_i64, _i64, _i64, _f, _vp, _i, _i64, _vp]),
     "cb_adamw": (_i, [_vp] * 5 + [_i64] + [_f] * 5 + [_i, _f, _vp]),
     "cb_adamw_ex": (_i, [_vp] * 5 + [_i64] + [_f] * 5 + [_i, _f, _vp, _i, _vp]),
     "cb_sumsq_bf16": (_i, [_vp, _i64, _vp, _vp, _i64, _i, _vp]),

@@ -476,7 +476,8 @@ class LMHeadLossFn(torch.autograd.Function):
         V = weight.shape[0]
         dev = hidden.device
         chunk = meta.get("chunk", 4096)
-        n_valid = meta["n_valid"]  # python int (known on the host from the collator) — no device sync
+        n_valid = meta["n_valid"]  # python int (host-side, from the collator) or None: counted on the device (inv_count_dev)
+        inv_dev = meta.get("inv_count_dev")   # fp32 [1] device tensor = 1 / max(#valid labels, 1) when n_valid is None
         train = meta["train"]
         p_w = meta["params"][0]
         _await(p_w)
@@ -506,7 +507,7 @@ class LMHeadLossFn(torch.autograd.Function):
         # `loss_scale` (TrainEngine: e.g. 1 / gradient_accumulation_steps) is folded into the gradients formed here; the
         # returned loss value is the unscaled mean.  The gradients are final when forward returns: backward() only hands
         # out dhidden, so `(loss * c).backward()` with c != 1 is NOT supported on this path (use loss_scale).
-        gscale = float(meta.get("loss_scale", 1.0)) / max(n_valid, 1)
+        gscale = float(meta.get("loss_scale", 1.0)) / (max(n_valid, 1) if n_valid is not None else 1)
         logits = torch.empty((min(chunk, rows), V), dtype=torch.bfloat16, device=dev)
         dw_local = None
         if need_dw and getattr(p_w, "main_grad", None) is None:
@@ -515,7 +516,8 @@ class LMHeadLossFn(torch.autograd.Function):
             r1 = min(rows, r0 + chunk)
             lg = logits[: r1 - r0]
             ops.gemm(h2[r0:r1], weight, out=lg)
-            ops.cross_entropy(lg, labels[r0:r1], loss_rows[r0:r1], acc, gscale, train)
+            ops.cross_entropy(lg, labels[r0:r1], loss_rows[r0:r1], acc, gscale, train,
+                              scale_dev=inv_dev if n_valid is None else None)
             if train:
                 ops.gemm(lg, weight, b_mn=True, out=dh[r0:r1])
                 if not need_dw:
@@ -537,7 +539,7 @@ class LMHeadLossFn(torch.autograd.Function):
         ctx.has_dw = dw_local is not None
         if train:
             ctx.save_for_backward(dh, *([dw_local] if dw_local is not None else []))
-        loss = acc[0] / max(n_valid, 1)
+        loss = acc[0] / max(n_valid, 1) if n_valid is not None else acc[0] * inv_dev[0]
         return loss
 
     @staticmethod

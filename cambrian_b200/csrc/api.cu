@@ -79,8 +79,8 @@ int group_colsum_launch(const void*, void*, float*, int, long long, int, float, 
 int group_broadcast_launch(const void*, void*, int, long long, int, float, int, cudaStream_t);
 int pos_grad_launch(const void*, void*, int, int, int, int, int, cudaStream_t);
 int f32_to_bf16_launch(const float*, void*, long long, int, long long, float, cudaStream_t);
-int cross_entropy_launch(void*, const long long*, float*, float*, long long, long long, long long, float, int,
-                         long long, cudaStream_t);
+int cross_entropy_launch(void*, const long long*, float*, float*, long long, long long, long long, float, const float*,
+                         int, long long, cudaStream_t);
 int adamw_launch(float*, float*, float*, const void*, void*, long long, float, float, float, float, float, int, float,
                  const float*, int, cudaStream_t);
 int sumsq_launch(const void*, long long, float*, float*, long long, int, cudaStream_t);
@@ -232,7 +232,13 @@ int cb_f32_to_bf16(const float* in, void* out, int64_t rows, int cols, int64_t o
 int cb_cross_entropy(void* logits, const int64_t* labels, float* loss_rows, float* loss_acc, int64_t rows, int64_t V,
                      int64_t ld, float grad_scale, int write_grad, int64_t ignore_index, void* stream) {
   return cb::cross_entropy_launch(logits, reinterpret_cast<const long long*>(labels), loss_rows, loss_acc, rows, V, ld,
-                                  grad_scale, write_grad, ignore_index, ST(stream));
+                                  grad_scale, nullptr, write_grad, ignore_index, ST(stream));
+}
+int cb_cross_entropy_ex(void* logits, const int64_t* labels, float* loss_rows, float* loss_acc, int64_t rows, int64_t V,
+                        int64_t ld, float grad_scale, const float* grad_scale_dev, int write_grad, int64_t ignore_index,
+                        void* stream) {
+  return cb::cross_entropy_launch(logits, reinterpret_cast<const long long*>(labels), loss_rows, loss_acc, rows, V, ld,
+                                  grad_scale, grad_scale_dev, write_grad, ignore_index, ST(stream));
 }
 int cb_span_gather(const void* hidden, void* lat, int B, int S, int H, int start, int q_side, void* stream) {
   return cb::span_gather_launch(hidden, lat, B, S, H, start, q_side, q_side, ST(stream));

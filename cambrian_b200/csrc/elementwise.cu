@@ -609,8 +609,10 @@ __global__ void span_scatter_kernel(bf16* __restrict__ hidden, const bf16* __res
 // shift, CrossEntropyLoss mean over non-ignored; the shift is done by the caller's label pointer).
 __global__ void __launch_bounds__(1024)
 cross_entropy_kernel(bf16* __restrict__ logits, const long long* __restrict__ labels, float* __restrict__ loss_rows,
-                     long long V, long long ld, float grad_scale, int write_grad, long long ignore_index) {
+                     long long V, long long ld, float grad_scale, const float* __restrict__ scale_dev, int write_grad,
+                     long long ignore_index) {
   __shared__ float red_m[32], red_s[32];
+  if (scale_dev) grad_scale *= __ldg(scale_dev);  // e.g. 1 / (number of valid labels), counted on the device: no host sync
   const long long row = blockIdx.x;
   bf16* lp = logits + row * ld;
   const long long label = labels[row];
@@ -958,12 +960,12 @@ int span_scatter_launch(void* hidden, const void* lat, int B, int S, int H, int 
   return CB_OK;
 }
 int cross_entropy_launch(void* logits, const long long* labels, float* loss_rows, float* loss_acc, long long rows,
-                         long long V, long long ld, float grad_scale, int write_grad, long long ignore_index,
-                         cudaStream_t st) {
+                         long long V, long long ld, float grad_scale, const float* scale_dev, int write_grad,
+                         long long ignore_index, cudaStream_t st) {
   CB_CHECK_ARG(V % 8 == 0 && ld % 8 == 0, "cross_entropy: vocab and ld must be multiples of 8");
   CB_CHECK_ARG(rows > 0, "cross_entropy: no rows");
-  cross_entropy_kernel<<<(unsigned)rows, 1024, 0, st>>>((bf16*)logits, labels, loss_rows, V, ld, grad_scale, write_grad,
-                                                       ignore_index);
+  cross_entropy_kernel<<<(unsigned)rows, 1024, 0, st>>>((bf16*)logits, labels, loss_rows, V, ld, grad_scale, scale_dev,
+                                                       write_grad, ignore_index);
   CB_CUDA_LAUNCH_CHECK("cross_entropy");
   if (loss_acc) {
     loss_reduce_kernel<<<1, 1024, 0, st>>>(loss_rows, labels, rows, V, ignore_index, loss_acc);

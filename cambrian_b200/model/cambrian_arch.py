@@ -333,19 +333,30 @@ class CambrianMetaForCausalLM(ABC):
         span = q_num + q_side
         # --- locate the image span of every sample; expand a bare <image> indicator the way the collator does
         #     (train_fsdp.py:1089-1165) when the caller passes un-expanded ids (inference path)
+        img_start = None
         if image_positions is not None:
             starts = [int(p) for p in image_positions]
+        elif getattr(cfg, "inputs_pre_expanded", False):
+            # the static-shape contract of the reference's training branch (IS_XLA_AVAILABLE side, cambrian_arch.py:457-490):
+            # the collator has already expanded <image> into the 600-slot span (train_fsdp.py:1089-1165).  The span start is
+            # then located ON THE DEVICE (index plumbing, no host sync); samples without an image get -1.
+            hit = input_ids == IMAGE_TOKEN_INDEX
+            img_start = torch.where(hit.any(1), hit.int().argmax(1), torch.full((bs,), -1, device=input_ids.device,
+                                                                                dtype=torch.long)).to(torch.int32)
         else:
             ids_cpu = input_ids.detach().to("cpu")
             if any(int((row == IMAGE_TOKEN_INDEX).sum()) > 1 for row in ids_cpu):
                 raise NotImplementedError("exactly one image per sample (train_fsdp.py:1100)")
-            needs_expand = False
+            flags = []          # per row with an image: is the <image> indicator still bare (needs the 600-slot expansion)?
             for row in ids_cpu:
                 pos = torch.where(row == IMAGE_TOKEN_INDEX)[0]
                 if len(pos) == 1:
                     p0 = int(pos[0])
-                    if p0 + span > row.shape[0] or bool((row[p0 + 1:p0 + span] != 0).any()):
-                        needs_expand = True
+                    flags.append(p0 + span > row.shape[0] or bool((row[p0 + 1:p0 + span] != 0).any()))
+            if any(flags) and not all(flags):
+                raise ValueError("a batch must hold either collator-expanded image spans or bare <image> indicators, not a "
+                                 "mix (pass image_positions, or expand every row)")
+            needs_expand = any(flags)
             if needs_expand:
                 input_ids, labels, attention_mask, position_ids = _expand_image_tokens(
                     ids_cpu, labels, attention_mask, span, input_ids.device)
@@ -354,7 +365,8 @@ class CambrianMetaForCausalLM(ABC):
             for row in ids_cpu:
                 pos = torch.where(row == IMAGE_TOKEN_INDEX)[0]
                 starts.append(int(pos[0]) if len(pos) else -1)
-        img_start = torch.tensor(starts, dtype=torch.int32).to(input_ids.device, non_blocking=True)
+        if img_start is None:
+            img_start = torch.tensor(starts, dtype=torch.int32).to(input_ids.device, non_blocking=True)
 
         feats = self.encode_images(images)                                                      # :366
         # (TrainEngine: the optimizer of the previous step may still be running on its side stream under the frozen towers

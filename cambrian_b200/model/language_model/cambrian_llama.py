@@ -359,18 +359,23 @@ class _CELossFn(torch.autograd.Function):
     """Shifted cross-entropy on materialised bf16 logits (API-compat path; training uses the fused LMHeadLossFn)."""
 
     @staticmethod
-    def forward(ctx, logits2d, shift_labels, n_valid):
+    def forward(ctx, logits2d, shift_labels, n_valid, inv_dev):
         buf = logits2d.clone()
         rows = buf.shape[0]
         loss_rows = torch.empty(rows, dtype=torch.float32, device=buf.device)
         acc = torch.zeros(2, dtype=torch.float32, device=buf.device)
-        ops.cross_entropy(buf, shift_labels, loss_rows, acc, 1.0 / max(n_valid, 1), True)
+        if n_valid is not None:
+            ops.cross_entropy(buf, shift_labels, loss_rows, acc, 1.0 / max(n_valid, 1), True)
+            loss = acc[0] / max(n_valid, 1)
+        else:       # count of valid labels stays on the device
+            ops.cross_entropy(buf, shift_labels, loss_rows, acc, 1.0, True, scale_dev=inv_dev)
+            loss = acc[0] * inv_dev[0]
         ctx.save_for_backward(buf)
-        return acc[0] / max(n_valid, 1)
+        return loss
 
     @staticmethod
     def backward(ctx, dloss):
-        return ctx.saved_tensors[0] * dloss.to(ctx.saved_tensors[0].dtype), None, None
+        return ctx.saved_tensors[0] * dloss.to(ctx.saved_tensors[0].dtype), None, None, None
 
 
 class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM):
@@ -423,24 +428,28 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
         loss = logits = None
         fused = bool(getattr(self.config, "fused_lm_loss", False))
         shift = None
+        inv_count_dev = None
         if labels is not None:
             shift = torch.full_like(labels, IGNORE_INDEX)
             shift[:, :-1] = labels[:, 1:]
             shift = shift.reshape(-1).contiguous()
             if num_valid_labels is None:
-                num_valid_labels = int(((shift != IGNORE_INDEX) & (shift >= 0) & (shift < self.vocab_size)).sum())
+                # mean over non-ignored labels (:411-422): the count stays on the device (no host sync per step)
+                cnt = ((shift != IGNORE_INDEX) & (shift >= 0) & (shift < self.vocab_size)).sum()
+                inv_count_dev = (1.0 / cnt.clamp(min=1).float()).reshape(1)
         if labels is not None and fused:
             # gradients are formed inside the fused forward: only when something will consume them (training mode, or no
             # TrainEngine buffers to write into) — an eval pass with labels under grad mode must not touch main_grad
             train = torch.is_grad_enabled() and (self.training or getattr(self.lm_head.weight, "main_grad", None) is None)
             meta = dict(shift_labels=shift, n_valid=num_valid_labels, train=train,
                         params=(self.lm_head.weight,), chunk=getattr(self.config, "lm_loss_chunk", 4096),
-                        label_ranges=label_ranges, loss_scale=getattr(self, "_cb_loss_scale", 1.0))
+                        label_ranges=label_ranges, loss_scale=getattr(self, "_cb_loss_scale", 1.0),
+                        inv_count_dev=inv_count_dev)
             loss = LMHeadLossFn.apply(meta, hidden, self.lm_head.weight)
         else:
             logits_bf16 = LinearFn.apply(hidden, self.lm_head.weight, None)                     # :408
             if labels is not None:
-                loss = _CELossFn.apply(logits_bf16.view(B * S, -1), shift, num_valid_labels)    # :411-422
+                loss = _CELossFn.apply(logits_bf16.view(B * S, -1), shift, num_valid_labels, inv_count_dev)   # :411-422
             logits = logits_bf16.float()                                                        # :409
         if return_dict is False:
             return tuple(v for v in (loss, logits, out.past_key_values) if v is not None)

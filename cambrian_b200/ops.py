@@ -420,10 +420,13 @@ def f32_to_bf16(src, dst, scale: float = 1.0, cols: int | None = None, out_ld: i
     return dst
 
 
-def cross_entropy(logits, labels, loss_rows, loss_acc, grad_scale: float, write_grad: bool, ignore_index: int = -100):
+def cross_entropy(logits, labels, loss_rows, loss_acc, grad_scale: float, write_grad: bool, ignore_index: int = -100,
+                  scale_dev=None):
+    """scale_dev: optional fp32 device tensor; its element 0 multiplies grad_scale on the device (1 / #valid labels)."""
     rows, V = logits.shape
-    check(_lib.load().cb_cross_entropy(ptr(logits), ptr(labels), ptr(loss_rows), ptr(loss_acc), rows, V, logits.stride(0),
-                                       float(grad_scale), int(write_grad), ignore_index, stream()), "cb_cross_entropy")
+    check(_lib.load().cb_cross_entropy_ex(ptr(logits), ptr(labels), ptr(loss_rows), ptr(loss_acc), rows, V,
+                                          logits.stride(0), float(grad_scale), ptr(scale_dev), int(write_grad), ignore_index,
+                                          stream()), "cb_cross_entropy_ex")
 
 
 def adamw(p32, m, v, g16, p16, lr, beta1, beta2, eps, wd, step: int, grad_scale: float = 1.0, clip_coef=None,

@@ -9,6 +9,9 @@ SVA.  Pure integer/bool index arithmetic; checked bit-exactly against fixtures g
 """
 from __future__ import annotations
 
+from dataclasses import dataclass
+from typing import Dict, Sequence
+
 import torch
 
 IGNORE_INDEX = -100
@@ -98,3 +101,64 @@ def valid_label_ranges(labels, ignore_index: int = IGNORE_INDEX):
     edges = np.flatnonzero(np.diff(np.concatenate([[0], valid.astype(np.int8), [0]])))
     ranges = [(int(a), int(b)) for a, b in zip(edges[0::2], edges[1::2])]
     return ranges, int(valid.sum())
+
+
+@dataclass
+class DataCollatorForSupervisedDataset(object):
+    """Mirror of train_fsdp.py:1168-1236: pads / truncates every sample to `tokenizer.model_max_length`, inserts a dummy
+    <image> indicator at `image_position` when a sample has none, expands the indicator into the 576 + 24 slot span and
+    emits ids, labels, attention mask, position ids, the per-tower window masks and the stacked per-tower images.
+
+    `emit_hints` (extension; default on): three host-side facts the collator has anyway travel with the batch as extra
+    keys of the dict that is splatted into `model(**batch)` — `num_valid_labels` (int), `image_positions` (list[int]) and
+    `label_ranges` (list[(row0, row1)] of flattened rows whose SHIFTED label is not ignore_index).  They save the model two
+    device->host syncs per step and let the fused lm_head + loss skip rows that cannot contribute; results are identical
+    with or without them (tests/test_modules_gpu.py::test_fused_loss_with_label_ranges_matches_full_rows)."""
+
+    tokenizer: object
+    image_token_len: int
+    image_aux_token_len_list: list
+    image_position: int
+    emit_hints: bool = True
+
+    def __call__(self, instances: Sequence[Dict]) -> Dict[str, torch.Tensor]:
+        input_ids, labels = tuple([inst[key] for inst in instances] for key in ("input_ids", "labels"))
+        max_length = self.tokenizer.model_max_length
+        pad_id = self.tokenizer.pad_token_id
+        left = self.tokenizer.padding_side == "left"
+
+        def fit(t, fill):
+            if t.shape[0] >= max_length:
+                return t[:max_length]
+            n = max_length - t.shape[0]
+            return torch.nn.functional.pad(t, (n, 0) if left else (0, n), "constant", fill)
+
+        input_ids = torch.stack([fit(t, pad_id) for t in input_ids])
+        labels = torch.stack([fit(t, IGNORE_INDEX) for t in labels])
+        attention_mask = input_ids.ne(pad_id)
+        p = self.image_position
+        for i in range(len(input_ids)):                     # dummy image for text-only samples (:1201-1217)
+            if (input_ids[i] == IMAGE_TOKEN_INDEX).sum() == 0:
+                for t, fill in ((input_ids, IMAGE_TOKEN_INDEX), (labels, IGNORE_INDEX), (attention_mask, False)):
+                    tmp = t[i].clone()
+                    tmp[p + 1:] = t[i, p:-1]
+                    tmp[p] = fill
+                    t[i] = tmp
+        image_sizes = [inst["image_size"] for inst in instances]
+        ids, labs, mask, pos, aux_masks = prepare_multimodal_data(input_ids, labels, attention_mask, image_sizes,
+                                                                  self.image_token_len, self.image_aux_token_len_list,
+                                                                  max_length)
+        batch = dict(input_ids=ids, labels=labs, attention_mask=mask, position_ids=pos,
+                     image_aux_attention_masks_list=aux_masks)
+        if "image_aux_list" in instances[0]:
+            per_tower = [list(x) for x in zip(*[inst["image_aux_list"] for inst in instances])]
+            if all(x is not None and x.shape == per_tower[0][0].shape for x in per_tower[0]):
+                batch["images"] = [torch.stack(x) for x in per_tower]
+            else:
+                batch["images"] = per_tower
+        if self.emit_hints:
+            ranges, n_valid = valid_label_ranges(labs)
+            batch["num_valid_labels"] = n_valid
+            batch["label_ranges"] = ranges
+            batch["image_positions"] = [int(torch.where(r == IMAGE_TOKEN_INDEX)[0][0]) for r in ids]
+        return batch

@@ -162,6 +162,11 @@ int cb_f32_to_bf16(const float* in, void* out, int64_t rows, int cols, int64_t o
  * with (softmax - onehot) * grad_scale. */
 int cb_cross_entropy(void* logits, const int64_t* labels, float* loss_rows, float* loss_acc, int64_t rows, int64_t V,
                      int64_t ld, float grad_scale, int write_grad, int64_t ignore_index, void* stream);
+/* same, with an additional gradient scale read from DEVICE memory (grad_scale_dev[0], may be NULL): the mean over
+ * non-ignored labels (cambrian_llama.py:411-422) without counting them on the host */
+int cb_cross_entropy_ex(void* logits, const int64_t* labels, float* loss_rows, float* loss_acc, int64_t rows, int64_t V,
+                        int64_t ld, float grad_scale, const float* grad_scale_dev, int write_grad, int64_t ignore_index,
+                        void* stream);
 /* in-LLM SVA site (cambrian_llama.py:168-207): gather the q*q latent rows of the image span [start, start+q*(q+1))
  * of hidden [B,S,H] into lat [B*q*q, H] / scatter updated rows back in place (newline rows untouched) */
 int cb_span_gather(const void* hidden, void* lat, int B, int S, int H, int start, int q_side, void* stream);
