@@ -82,6 +82,57 @@ def vgrad(param: torch.Tensor, g: torch.Tensor):
     return g
 
 
+def _uniform_stack(tensors):
+    """If the given equally-shaped 2-D contiguous tensors sit at one constant positive stride in a common storage (the K/V
+    projection weights of an SVA layer inside the TrainEngine's flat buffer do: named_parameters() lays them out as
+    ln.weight, ln.bias, linear.weight, repeated), return a [n, rows, cols] view over them — a batched GEMM operand without
+    any copy.  None otherwise."""
+    t0 = tensors[0]
+    if len(tensors) < 2 or any(t.shape != t0.shape or not t.is_contiguous() or t.dtype != t0.dtype for t in tensors):
+        return None
+    st = t0.untyped_storage().data_ptr()
+    if any(t.untyped_storage().data_ptr() != st for t in tensors):
+        return None
+    es = t0.element_size()
+    d = (tensors[1].data_ptr() - t0.data_ptr()) // es
+    if d <= 0 or (d * es) % 16 or any((tensors[i + 1].data_ptr() - tensors[i].data_ptr()) != d * es for i in range(len(tensors) - 1)):
+        return None
+    return torch.as_strided(t0, (len(tensors), t0.shape[0], t0.shape[1]), (d, t0.stride(0), 1))
+
+
+def _kv_groups(feats):
+    """Towers with the same number of feature rows share one batched launch (BASELINE grids: all four; release grids
+    [576, 576, 576, 9216]: the three small ones, the ConvNeXt grid alone)."""
+    groups = {}
+    for i, f in enumerate(feats):
+        groups.setdefault(f.shape[0], []).append(i)
+    return list(groups.values())
+
+
+def wgrad_batched(params, dy_stack, x_stack):
+    """dW_j = dy_stack[j]^T @ x_stack[j] for a group of equally-shaped weights in ONE batched launch.  With TrainEngine
+    buffers the results accumulate straight into the (uniformly strided) main_grad slices; otherwise the list of gradient
+    tensors is returned.  Falls back to one launch per weight when the layout / state does not allow batching."""
+    n = len(params)
+    if all(_frozen(p) for p in params):
+        return [None] * n
+    mgs = [getattr(p, "main_grad", None) for p in params]
+    if all(m is None for m in mgs) and not any(_frozen(p) for p in params):
+        dw = ops.gemm(dy_stack, x_stack, a_mn=True, b_mn=True)
+        return [dw[j] for j in range(n)]
+    if all(m is not None for m in mgs) and not any(_frozen(p) for p in params):
+        firsts = [p._cb_fresh is not None and "all" not in p._cb_fresh for p in params]
+        mstack = _uniform_stack(mgs)
+        if mstack is not None and (all(firsts) or not any(firsts)):
+            ops.gemm(dy_stack, x_stack, a_mn=True, b_mn=True, out=mstack, accumulate=not firsts[0])
+            for p in params:
+                if p._cb_fresh is not None:
+                    p._cb_fresh.add("all")
+                _notify(p)
+            return [None] * n
+    return [wgrad(p, dy_stack[j], x_stack[j]) for j, p in enumerate(params)]
+
+
 def _merge_wgrad(parts):
     """Assemble a full-weight gradient from column blocks when no main_grad buffer exists."""
     return torch.cat(parts, dim=1)
@@ -201,19 +252,37 @@ class SVALayerFn(torch.autograd.Function):
         qin = ops.f32_to_bf16(t32, torch.empty((N, t32.shape[1]), dtype=torch.bfloat16, device=queries.device))
         qn, mq, rq = ops.layernorm_fwd(qin, P["q_ln_w"], P["q_ln_b"], 1e-5, save_stats=True)
         Q = ops.gemm(qn, P["q_w"])
-        kins, vins, stats, Ks, Vs = [], [], [], [], []
-        for i in range(T):
-            r = rs[i]
-            pos = P.get(f"pos_embed_{i}") if r > 1 else None
-            side = 0 if windowed else r * q_side
-            kin, mean, rstd = ops.layernorm_fwd(feats[i], P[f"k_ln_w_{i}"], P[f"k_ln_b_{i}"], 1e-5, pos=pos, side=side, r=r,
-                                                save_stats=True)
-            vin = ops.layernorm_fwd(feats[i], P[f"v_ln_w_{i}"], P[f"v_ln_b_{i}"], 1e-5, pos=pos, side=side, r=r)
-            kins.append(kin)
-            vins.append(vin)
-            stats += [mean, rstd]
-            Ks.append(ops.gemm(kin, P[f"k_w_{i}"]))
-            Vs.append(ops.gemm(vin, P[f"v_w_{i}"]))
+        # K/V projections (vision_sampler.py:187-189: a per-tower list comprehension of LayerNorm + Linear).  Towers with equal
+        # row counts are ONE batched GEMM [2g, rows, 1024] x [2g, 1024, 1024]: the 2g LayerNorm outputs are written into one
+        # buffer, the 2g weights are read in place through a strided view when they sit at a uniform stride (TrainEngine
+        # flat buffer) — 8 sub-wave launches of 144 tiles become one launch of 1152 tiles.
+        kins, vins, stats, Ks, Vs = [None] * T, [None] * T, [None] * (2 * T), [None] * T, [None] * T
+        kv_w = []          # per group: the stacked-weight view (saved for backward) or None
+        for grp in _kv_groups(feats):
+            g = len(grp)
+            rows = feats[grp[0]].shape[0]
+            wstack = _uniform_stack([P[f"{kv}_w_{i}"] for i in grp for kv in ("k", "v")]) if g > 1 else None
+            kv_w.append(wstack)
+            xin = torch.empty((2 * g, rows, feats[grp[0]].shape[1]), dtype=torch.bfloat16, device=queries.device) \
+                if wstack is not None else None
+            for j, i in enumerate(grp):
+                r = rs[i]
+                pos = P.get(f"pos_embed_{i}") if r > 1 else None
+                side = 0 if windowed else r * q_side
+                kin, mean, rstd = ops.layernorm_fwd(feats[i], P[f"k_ln_w_{i}"], P[f"k_ln_b_{i}"], 1e-5, pos=pos, side=side,
+                                                    r=r, save_stats=True, out=None if xin is None else xin[2 * j])
+                vin = ops.layernorm_fwd(feats[i], P[f"v_ln_w_{i}"], P[f"v_ln_b_{i}"], 1e-5, pos=pos, side=side, r=r,
+                                        out=None if xin is None else xin[2 * j + 1])
+                kins[i], vins[i] = kin, vin
+                stats[2 * i], stats[2 * i + 1] = mean, rstd
+            if wstack is not None:
+                kv = ops.gemm(xin, wstack)                       # [2g, rows, 1024]
+                for j, i in enumerate(grp):
+                    Ks[i], Vs[i] = kv[2 * j], kv[2 * j + 1]
+            else:
+                for i in grp:
+                    Ks[i] = ops.gemm(kins[i], P[f"k_w_{i}"])
+                    Vs[i] = ops.gemm(vins[i], P[f"v_w_{i}"])
         A, lse = ops.sva_window_attn_fwd(Q, Ks, Vs, masks, rs, B, q_side, need_lse=True, windowed=windowed)
         q2 = ops.gemm(A, P["o_w"], residual=qin)
         q3, m3, r3 = ops.layernorm_fwd(q2, P["norm_w"], P["norm_b"], 1e-5, save_stats=True)
@@ -256,33 +325,61 @@ class SVALayerFn(torch.autograd.Function):
         g["norm_w"], g["norm_b"] = vgrad(prm["norm_w"], dgn), vgrad(prm["norm_b"], dbn)
         dA = ops.gemm(dq2, P["o_w"], b_mn=True)
         g["o_w"] = wgrad(prm["o_w"], dq2, A)
-        dQ, dKs, dVs = ops.sva_window_attn_bwd(Q, A, dA, lse, list(Ks), list(Vs), masks, rs, B, q_side, windowed=windowed)
+        # dK / dV land in one stacked buffer per equal-row group so that dX = dKV @ W and dW = dKV^T @ X are batched launches
+        groups = _kv_groups(feats)
+        stacks = {}
+        dKs, dVs = [None] * T, [None] * T
+        for grp in groups:
+            g = len(grp)
+            wstack = _uniform_stack([P[f"{kv}_w_{i}"] for i in grp for kv in ("k", "v")]) if g > 1 else None
+            xstack = _uniform_stack([t for i in grp for t in (kins[i], vins[i])]) if wstack is not None else None
+            if wstack is not None and xstack is not None:
+                dkv = torch.empty((2 * g,) + tuple(Ks[grp[0]].shape), dtype=torch.bfloat16, device=dout.device)
+                for j, i in enumerate(grp):
+                    dKs[i], dVs[i] = dkv[2 * j], dkv[2 * j + 1]
+                stacks[grp[0]] = (wstack, xstack, dkv)
+            else:
+                for i in grp:
+                    dKs[i], dVs[i] = torch.empty_like(Ks[i]), torch.empty_like(Vs[i])
+        dQ, _, _ = ops.sva_window_attn_bwd(Q, A, dA, lse, list(Ks), list(Vs), masks, rs, B, q_side, windowed=windowed,
+                                           dks=dKs, dvs=dVs)
         dqn = ops.gemm(dQ, P["q_w"], b_mn=True)
         g["q_w"] = wgrad(prm["q_w"], dQ, qn)
         dqin, dgq, dbq = ops.layernorm_bwd(dqn, qin, P["q_ln_w"], mq, rq, dres=dq2)
         g["q_ln_w"], g["q_ln_b"] = vgrad(prm["q_ln_w"], dgq), vgrad(prm["q_ln_b"], dbq)
-        dfeats = []
-        for i in range(T):
-            r = rs[i]
-            pos = P.get(f"pos_embed_{i}") if r > 1 else None
-            side = 0 if windowed else r * q_side
-            mean, rstd = stats[2 * i], stats[2 * i + 1]
-            dkin = ops.gemm(dKs[i], P[f"k_w_{i}"], b_mn=True)
-            g[f"k_w_{i}"] = wgrad(prm[f"k_w_{i}"], dKs[i], kins[i])
-            dvin = ops.gemm(dVs[i], P[f"v_w_{i}"], b_mn=True)
-            g[f"v_w_{i}"] = wgrad(prm[f"v_w_{i}"], dVs[i], vins[i])
-            dxk, dgk, dbk = ops.layernorm_bwd(dkin, feats[i], P[f"k_ln_w_{i}"], mean, rstd, pos=pos, side=side, r=r)
-            dxv, dgv, dbv = ops.layernorm_bwd(dvin, feats[i], P[f"v_ln_w_{i}"], mean, rstd, pos=pos, side=side, r=r,
-                                              dres=dxk)
-            g[f"k_ln_w_{i}"], g[f"k_ln_b_{i}"] = vgrad(prm[f"k_ln_w_{i}"], dgk), vgrad(prm[f"k_ln_b_{i}"], dbk)
-            g[f"v_ln_w_{i}"], g[f"v_ln_b_{i}"] = vgrad(prm[f"v_ln_w_{i}"], dgv), vgrad(prm[f"v_ln_b_{i}"], dbv)
-            if r > 1:
-                if windowed:
-                    dp = ops.pos_grad(dxv, dxv.shape[0] // (r * r), r, r)
+        dfeats = [None] * T
+        for grp in groups:
+            batched = stacks.get(grp[0])
+            if batched is not None:
+                wstack, xstack, dkv = batched
+                dxin = ops.gemm(dkv, wstack, b_mn=True)                                  # [2g, rows, 1024]
+                names = [f"{kv}_w_{i}" for i in grp for kv in ("k", "v")]
+                for nme, gw in zip(names, wgrad_batched([prm[nme] for nme in names], dkv, xstack)):
+                    g[nme] = gw
+            for j, i in enumerate(grp):
+                r = rs[i]
+                pos = P.get(f"pos_embed_{i}") if r > 1 else None
+                side = 0 if windowed else r * q_side
+                mean, rstd = stats[2 * i], stats[2 * i + 1]
+                if batched is not None:
+                    dkin, dvin = dxin[2 * j], dxin[2 * j + 1]
                 else:
-                    dp = ops.pos_grad(dxv, B, r * q_side, r)
-                g[f"pos_embed_{i}"] = vgrad(prm[f"pos_embed_{i}"], dp)
-            dfeats.append(dxv)
+                    dkin = ops.gemm(dKs[i], P[f"k_w_{i}"], b_mn=True)
+                    g[f"k_w_{i}"] = wgrad(prm[f"k_w_{i}"], dKs[i], kins[i])
+                    dvin = ops.gemm(dVs[i], P[f"v_w_{i}"], b_mn=True)
+                    g[f"v_w_{i}"] = wgrad(prm[f"v_w_{i}"], dVs[i], vins[i])
+                dxk, dgk, dbk = ops.layernorm_bwd(dkin, feats[i], P[f"k_ln_w_{i}"], mean, rstd, pos=pos, side=side, r=r)
+                dxv, dgv, dbv = ops.layernorm_bwd(dvin, feats[i], P[f"v_ln_w_{i}"], mean, rstd, pos=pos, side=side, r=r,
+                                                  dres=dxk)
+                g[f"k_ln_w_{i}"], g[f"k_ln_b_{i}"] = vgrad(prm[f"k_ln_w_{i}"], dgk), vgrad(prm[f"k_ln_b_{i}"], dbk)
+                g[f"v_ln_w_{i}"], g[f"v_ln_b_{i}"] = vgrad(prm[f"v_ln_w_{i}"], dgv), vgrad(prm[f"v_ln_b_{i}"], dbv)
+                if r > 1:
+                    if windowed:
+                        dp = ops.pos_grad(dxv, dxv.shape[0] // (r * r), r, r)
+                    else:
+                        dp = ops.pos_grad(dxv, B, r * q_side, r)
+                    g[f"pos_embed_{i}"] = vgrad(prm[f"pos_embed_{i}"], dp)
+                dfeats[i] = dxv
         dqueries = ops.gemm(dqin, P["proj_in"][:, :D], b_mn=True, residual=dout)
         dctxp = ops.gemm(dqin, P["proj_in"][:, D:], b_mn=True)
         w_in = prm["proj_in"]

@@ -84,6 +84,7 @@ int cross_entropy_launch(void*, const long long*, float*, float*, long long, lon
 int adamw_launch(float*, float*, float*, const void*, void*, long long, float, float, float, float, float, int, float,
                  const float*, int, cudaStream_t);
 int sumsq_launch(const void*, long long, float*, float*, long long, int, cudaStream_t);
+int gemm_set_dynamic_scheduling(int);
 int clip_coef_launch(float*, float, float, float*, cudaStream_t);
 int span_gather_launch(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int span_scatter_launch(void*, const void*, int, int, int, int, int, int, cudaStream_t);
@@ -294,6 +295,7 @@ int cb_adamw_ex(float* p, float* m, float* v, const void* g, void* p16, int64_t 
   return cb::adamw_launch(p, m, v, g, p16, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, clip_coef, background,
                           ST(stream));
 }
+int cb_gemm_set_dynamic_scheduling(int on) { return cb::gemm_set_dynamic_scheduling(on); }
 int cb_sumsq_bf16(const void* g, int64_t n, float* acc, float* workspace, int64_t workspace_floats, int background,
                   void* stream) {
   return cb::sumsq_launch(g, n, acc, workspace, workspace_floats, background, ST(stream));

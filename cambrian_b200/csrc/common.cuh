@@ -374,6 +374,47 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
 }
 
 // ----------------------------------------------------------------------------------
+// Cluster Launch Control (sm_100): a running CTA asks the hardware work distributor to CANCEL a not-yet-launched
+// CTA / cluster of its own grid and takes over that block index.  A grid of one CTA per output tile then behaves like a
+// persistent kernel with a hardware tile queue: SMs that are busy with somebody else's kernel (an NCCL collective, an
+// optimizer grid) simply never receive a CTA and their share of the tiles is picked up by the SMs that are free.
+// PTX forms as in the vendored CUTLASS (cutlass/gemm/kernel/sm100_tile_scheduler.hpp: issue_clc_query /
+// work_tile_info_from_clc_response).
+// ----------------------------------------------------------------------------------
+// asynchronous: writes a 16-byte response to `resp` (this CTA) and completes 16 tx bytes on `bar`
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp, uint32_t bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(resp),
+               "r"(bar)
+               : "memory");
+}
+// cluster variant: response + completion are multicast to the same offsets in EVERY CTA of the cluster
+__device__ __forceinline__ void clc_try_cancel_multicast(uint32_t resp, uint32_t bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];" ::
+          "r"(resp),
+      "r"(bar)
+      : "memory");
+}
+// decode a response: blockIdx.x of the cancelled CTA (first CTA of the cancelled cluster), or -1 if nothing was left
+__device__ __forceinline__ int clc_decode(uint32_t resp) {
+  uint32_t x = 0, y = 0, z = 0, ok = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p1;\n"
+      ".reg .b128 clc_result;\n"
+      "ld.shared.b128 clc_result, [%4];\n"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, clc_result;\n"
+      "selp.u32 %3, 1, 0, p1;\n"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, clc_result;\n"
+      "}\n"
+      : "=r"(x), "=r"(y), "=r"(z), "=r"(ok)
+      : "r"(resp)
+      : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic read ordered before the next async write
+  return ok ? static_cast<int>(x) : -1;
+}
+
+// ----------------------------------------------------------------------------------
 // UMMA descriptors (SWIZZLE_128B canonical layouts, bf16)
 //
 // K-major tile (rows = M or N, 64 bf16 = 128 B of K per row, rows packed at 128 B):

@@ -43,6 +43,7 @@ struct GemmEpilogue {
   int tma_store;   // bf16 output without accumulate: tiles leave through smem staging + TMA stores (tmC / tmAux)
   void* aux;       // ACT_SWIGLU_PAIR: second output, silu(gate) * up, [M, N / 2] bf16
   long long ld_aux;
+  int dyn;         // 1: one CTA (pair) per tile in the grid, tiles handed out by Cluster Launch Control (TileRing below)
 };
 constexpr int ACT_SWIGLU_PAIR = 5;  // CTA-pair kernel only: the tile's two B halves are gate rows and the matching up rows
 
@@ -84,6 +85,65 @@ __device__ __forceinline__ void tile_to_mn(int r, int m_blocks, int n_blocks, in
   const int w = r - g * tpg;
   mb = first + w % gs;
   nb = w / gs;
+}
+
+// ------------------------------------------------------------------------------------------
+// Dynamic tile scheduling (ep.dyn).  The grid holds ONE CTA (CTA pair) PER TILE.  A CTA that gets to run works on its own
+// block index first; its TMA-producer thread then keeps asking Cluster Launch Control to cancel a still-pending CTA of the
+// grid and processes that CTA's tile instead (common.cuh: clc_*), until nothing is pending.  Each tile id is handed to the
+// CTA's other roles (MMA issuer, 8 epilogue warps) through an 8-slot shared-memory ring guarded by full / empty mbarriers;
+// -1 ends every role's loop.  Compared with the static `tile += gridDim.x` walk of a 148-CTA persistent grid this makes
+// the GEMM indifferent to SMs it does not get: when an NCCL collective or the background optimizer holds some SMs, fewer
+// CTAs become resident and the resident ones simply take more tiles, instead of a late CTA still owning 1/148 of the
+// work (r01: that cost the full all-reduce time at every N, SCALE_r01).  The CLC query for the NEXT tile is in flight
+// while the current tile's operands stream in.
+// ------------------------------------------------------------------------------------------
+constexpr int RING = 8;
+struct TileRing {
+  uint32_t ids, full, empty, resp, clc_bar, clc_empty;
+};
+__device__ __forceinline__ TileRing make_ring(uint32_t bar_base) {
+  TileRing r;
+  r.ids = bar_base + 256u;         // int[RING]
+  r.full = bar_base + 320u;        // mbarrier[RING], 1 arrival (producer thread)
+  r.empty = bar_base + 384u;       // mbarrier[RING], 9 arrivals (MMA-warp lane + 8 epilogue warps)
+  r.resp = bar_base + 512u;        // 16-byte CLC response
+  r.clc_bar = bar_base + 528u;     // mbarrier: CLC response landed (16 tx bytes)
+  r.clc_empty = bar_base + 536u;   // pair kernel, leader's copy: the peer CTA has decoded the previous response
+  return r;
+}
+__device__ __forceinline__ void ring_init(const TileRing& r) {
+  for (int s = 0; s < RING; ++s) {
+    mbar_init(r.full + 8u * s, 1);
+    mbar_init(r.empty + 8u * s, 9);
+  }
+  mbar_init(r.clc_bar, 1);
+  mbar_init(r.clc_empty, 1);
+}
+__device__ __forceinline__ void ring_publish(const TileRing& r, int it, int tile) {
+  const int s = it & (RING - 1);
+  mbar_wait(r.empty + 8u * s, static_cast<uint32_t>(((it / RING) & 1) ^ 1));
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(r.ids + 4u * s), "r"(tile) : "memory");
+  mbar_arrive(r.full + 8u * s);  // release: the id is visible to whoever observes the phase
+}
+// one thread
+__device__ __forceinline__ int ring_fetch(const TileRing& r, int it) {
+  const int s = it & (RING - 1);
+  mbar_wait(r.full + 8u * s, static_cast<uint32_t>((it / RING) & 1));
+  int t;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(r.ids + 4u * s) : "memory");
+  mbar_arrive(r.empty + 8u * s);
+  return t;
+}
+// whole warp (every lane needs the id); one arrival per warp
+__device__ __forceinline__ int ring_fetch_warp(const TileRing& r, int it, int lane) {
+  const int s = it & (RING - 1);
+  mbar_wait(r.full + 8u * s, static_cast<uint32_t>((it / RING) & 1));
+  int t;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(r.ids + 4u * s) : "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive(r.empty + 8u * s);
+  return t;
 }
 
 // Epilogue of one accumulator tile for the 32-column chunks [c_begin, c_end) owned by this warp:
@@ -389,8 +449,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 8);  // one arrive per epilogue warp
     }
+    ring_init(make_ring(bar_base));
     mbar_fence_init();
   }
+  const TileRing ring = make_ring(bar_base);
+  const bool dyn = ep.dyn != 0;
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -402,8 +465,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ============================ TMA producer ============================
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      uint32_t phase = 0, clc_phase = 0;
+      int it = 0;
+      int tile = blockIdx.x;
+      while (true) {
+        if (dyn) ring_publish(ring, it, tile);
+        if (tile < 0) break;
+        if (dyn) {  // ask for the next tile now; the answer arrives while this tile's operands stream in
+          mbar_arrive_expect_tx(ring.clc_bar, 16);
+          clc_try_cancel(ring.resp, ring.clc_bar);
+        }
         const int b = tile / tiles_per_batch;
         const int r = tile - b * tiles_per_batch;
         int mb_, nb_;
@@ -435,6 +506,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             phase ^= 1u;
           }
         }
+        if (dyn) {
+          mbar_wait(ring.clc_bar, clc_phase);
+          clc_phase ^= 1u;
+          tile = clc_decode(ring.resp);  // blockIdx.x of the cancelled CTA == its tile; -1: the grid is exhausted
+          ++it;
+        } else {
+          tile += gridDim.x;
+          if (tile >= num_tiles) break;
+        }
       }
     }
   } else if (warp == 1) {
@@ -445,7 +525,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = dyn ? ring_fetch(ring, 0) : (int)blockIdx.x; tile >= 0 && tile < num_tiles;
+           tile = dyn ? ring_fetch(ring, ++it) : tile + (int)gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -481,8 +563,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int col_half = (warp - 2) >> 2;  // warps 2-5: first half of the tile's columns, warps 6-9: second half
     int acc = 0;
     uint32_t acc_phase = 0;
-    StageRing ring{bar_base + 1024u + static_cast<uint32_t>(warp - 2) * 4096u, 0};
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    StageRing sring{bar_base + 1024u + static_cast<uint32_t>(warp - 2) * 4096u, 0};
+    int it = 0;
+    for (int tile = dyn ? ring_fetch_warp(ring, 0, lane) : (int)blockIdx.x; tile >= 0 && tile < num_tiles;
+         tile = dyn ? ring_fetch_warp(ring, ++it, lane) : tile + (int)gridDim.x) {
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
       int mb_, nb_;
@@ -495,7 +579,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const bool row_ok = row < M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
-      epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64), ring, &tmC,
+      epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64), sring, &tmC,
                                 m0 + lane_grp * 32, lane);
       tc_fence_before();
       __syncwarp();
@@ -573,8 +657,11 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 16);  // 8 epilogue warps x 2 CTAs arrive on the leader's copy
     }
+    ring_init(make_ring(bar_base));
     mbar_fence_init();
   }
+  const TileRing ring = make_ring(bar_base);
+  const bool dyn = ep.dyn != 0;
   if (warp == 1) tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   cluster_sync_all();  // barrier inits + TMEM allocation of both CTAs visible before any cross-CTA traffic
@@ -586,8 +673,22 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ============================ TMA producer (both CTAs) ============================
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      uint32_t phase = 0, clc_phase = 0;
+      int it = 0;
+      int tile = cluster_id;
+      while (true) {
+        if (dyn) ring_publish(ring, it, tile);  // each CTA's producer feeds its own CTA's MMA / epilogue warps
+        if (tile < 0) break;
+        if (dyn) {
+          // one query per cluster, issued by the leader, answered into BOTH CTAs' response slot / barrier (multicast);
+          // every CTA arms its own barrier.  The slot is single-buffered: the leader waits until the peer has decoded the
+          // previous answer (clc_empty, remote arrive below) before it lets the next one land.
+          mbar_arrive_expect_tx(ring.clc_bar, 16);
+          if (leader) {
+            if (it > 0) mbar_wait(ring.clc_empty, static_cast<uint32_t>((it - 1) & 1));
+            clc_try_cancel_multicast(ring.resp, ring.clc_bar);
+          }
+        }
         const int b = tile / tiles_per_batch;
         const int r = tile - b * tiles_per_batch;
         int mb_, nb_;
@@ -620,17 +721,35 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
             phase ^= 1u;
           }
         }
+        if (dyn) {
+          mbar_wait(ring.clc_bar, clc_phase);
+          clc_phase ^= 1u;
+          const int x = clc_decode(ring.resp);  // blockIdx.x of the cancelled cluster's first CTA
+          tile = x < 0 ? -1 : (x >> 1);
+          if (!leader) mbar_arrive_cluster(ring.clc_empty, 0);
+          ++it;
+        } else {
+          tile += num_clusters;
+          if (tile >= num_tiles) break;
+        }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer (leader CTA only) ========================
+    if (!leader && lane == 0 && dyn) {
+      // the peer's MMA warp has no MMAs to issue; it only takes its share of the ring's `empty` arrivals
+      for (int it = 0; ring_fetch(ring, it) >= 0; ++it) {
+      }
+    }
     if (leader && lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int it = 0;
+      for (int tile = dyn ? ring_fetch(ring, 0) : cluster_id; tile >= 0 && tile < num_tiles;
+           tile = dyn ? ring_fetch(ring, ++it) : tile + num_clusters) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -666,8 +785,10 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int col_half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    StageRing ring{bar_base + 1024u + static_cast<uint32_t>(warp - 2) * 4096u, 0};
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    StageRing sring{bar_base + 1024u + static_cast<uint32_t>(warp - 2) * 4096u, 0};
+    int it = 0;
+    for (int tile = dyn ? ring_fetch_warp(ring, 0, lane) : cluster_id; tile >= 0 && tile < num_tiles;
+         tile = dyn ? ring_fetch_warp(ring, ++it, lane) : tile + num_clusters) {
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
       int mb_, nb_;
@@ -681,9 +802,9 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) +
                              static_cast<uint32_t>(acc * BN);
       if constexpr (ACT == ACT_SWIGLU_PAIR)
-        epilogue_swiglu_pair(ep, taddr, row, row_ok, nb_, N, col_half, ring, &tmC, &tmAux, m0 + lane_grp * 32, lane);
+        epilogue_swiglu_pair(ep, taddr, row, row_ok, nb_, N, col_half, sring, &tmC, &tmAux, m0 + lane_grp * 32, lane);
       else
-        epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64), ring, &tmC,
+        epilogue_columns<BN, ACT>(ep, taddr, row, row_ok, b, n0, N, col_half * (BN / 64), sring, &tmC,
                                   m0 + lane_grp * 32, lane);
       tc_fence_before();
       __syncwarp();
@@ -790,7 +911,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     attr_set = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * batch;
-  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  const int grid = (ep.dyn || tiles < device_sm_count()) ? tiles : device_sm_count();
   kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, batch, ep);
   CB_CUDA_LAUNCH_CHECK("gemm_bf16_tcgen05");
   return CB_OK;
@@ -809,7 +930,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   }
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN) * batch;
   const int pairs = device_sm_count() / 2;
-  const int clusters = tiles < pairs ? tiles : pairs;
+  const int clusters = (ep.dyn || tiles < pairs) ? tiles : pairs;
   kern<<<2 * clusters, 320, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, tmAux, M, N, K, batch, ep);
   CB_CUDA_LAUNCH_CHECK("gemm_bf16_tcgen05_2cta");
   return CB_OK;
@@ -830,6 +951,22 @@ static int dispatch_2cta(int a_mn, int b_mn, const CUtensorMap& tmA, const CUten
   if (!a_mn && b_mn) return launch_gemm2<256, false, true, 0>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
   if (a_mn && !b_mn) return launch_gemm2<256, true, false, 0>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
   return launch_gemm2<256, true, true, 0>(tmA, tmB, tmC, tmC, M, N, K, batch, ep, stream);
+}
+
+// CB_GEMM_CLC=0 keeps the static persistent tile walk (read once); default: dynamic scheduling through Cluster Launch
+// Control whenever a GEMM has more tiles than one wave
+static int g_clc = -1;
+static bool clc_enabled() {
+  if (g_clc < 0) {
+    const char* e = getenv("CB_GEMM_CLC");
+    g_clc = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_clc == 1;
+}
+int gemm_set_dynamic_scheduling(int on) {  // returns the previous setting (A/B comparisons inside one process)
+  const int prev = clc_enabled() ? 1 : 0;
+  g_clc = on ? 1 : 0;
+  return prev;
 }
 
 // CB_GEMM_2CTA=0 disables the CTA-pair kernel (read once)
@@ -904,6 +1041,12 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int ba
   ep.ldr = ldr; ep.bsr = bsr;
   ep.alpha = alpha; ep.act = act; ep.out_fp32 = out_fp32; ep.accumulate = accumulate;
   ep.aux = nullptr; ep.ld_aux = 0;
+  {
+    // dynamic scheduling only pays (and only differs) when the static grid would be persistent: more tiles than SMs
+    const long long t = use_2cta ? (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + bn - 1) / bn) * batch * 2
+                                 : (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * batch;
+    ep.dyn = (clc_enabled() && t > device_sm_count()) ? 1 : 0;
+  }
   const int cvec = out_fp32 ? 4 : 8;
   bool vec = (N % 8 == 0) && (ldc % cvec == 0) && (bsc % cvec == 0) &&
              ((reinterpret_cast<uintptr_t>(C) & 15u) == 0);
@@ -955,6 +1098,7 @@ int gemm_swiglu_bf16(const void* A, const void* W, void* gu_out, void* act_out, 
   ep.bias = nullptr; ep.colscale = nullptr; ep.residual = nullptr; ep.ldr = 0; ep.bsr = 0;
   ep.alpha = 1.0f; ep.act = ACT_SWIGLU_PAIR; ep.out_fp32 = 0; ep.accumulate = 0; ep.vec_ok = 1;
   ep.aux = act_out; ep.ld_aux = ld_act;
+  ep.dyn = (clc_enabled() && 2LL * ((M + 2 * BM - 1) / (2 * BM)) * (N / 256) > device_sm_count()) ? 1 : 0;
   CUtensorMap tmC, tmAux;
   memset(&tmC, 0, sizeof(tmC));
   memset(&tmAux, 0, sizeof(tmAux));

@@ -459,22 +459,22 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
     @torch.no_grad()
     def generate(self, inputs: Optional[torch.Tensor] = None, images: Optional[torch.Tensor] = None,
                  image_sizes: Optional[torch.Tensor] = None, **kwargs):
-        """cambrian_llama.py:437-483: multimodal prefill once (towers + SVA), then greedy KV-cache decoding.
-        Supported kwargs: max_new_tokens, eos_token_id, pad_token_id, attention_mask, position_ids, do_sample=False /
-        temperature=0 (greedy).  Returns the newly generated ids [B, T] like HF generate does for `inputs_embeds`."""
+        """cambrian_llama.py:437-483: multimodal prefill once (towers + connector + SVA sites), then KV-cache decoding.
+
+        The reference hands `inputs_embeds` to HF `GenerationMixin.generate`; the subset of that API its callers use is
+        implemented here (cambrian_b200/generation.py): greedy or temperature / top-k / top-p sampling, `eos_token_id`,
+        `pad_token_id`, `max_new_tokens` / `max_length`, `stopping_criteria`, `streamer`, `attention_mask`,
+        `position_ids`, `generation_config`, `generator`.  Any other keyword is rejected unless it carries its neutral
+        value (num_beams=1, use_cache=True, ...).  Returns the newly generated ids [B, T], as HF does when generation
+        starts from `inputs_embeds`."""
+        from ...generation import GenerationArgs, next_tokens, should_stop
         if "inputs_embeds" in kwargs:
             raise NotImplementedError("`inputs_embeds` is not supported")                       # :447-448
         sync = getattr(self, "_cb_param_sync", None)
         if sync is not None:
             sync()      # a TrainEngine with deferred parameter sync: inference kernels read parameters directly
-        if kwargs.get("do_sample", False) and kwargs.get("temperature", 1.0) not in (0, 0.0):
-            raise NotImplementedError("only greedy decoding is implemented")
-        max_new = int(kwargs.get("max_new_tokens", 32))
-        eos = kwargs.get("eos_token_id", getattr(self.config, "eos_token_id", None))
-        eos = set(eos) if isinstance(eos, (list, tuple)) else ({eos} if eos is not None else set())
-        pad = kwargs.get("pad_token_id", getattr(self.config, "pad_token_id", None) or 0)
-        attention_mask = kwargs.get("attention_mask", None)
-        position_ids = kwargs.get("position_ids", None)
+        attention_mask = kwargs.pop("attention_mask", None)
+        position_ids = kwargs.pop("position_ids", None)
         was_training = self.training
         self.eval()
         feats = masks = final_size = ctx_feat = None
@@ -486,6 +486,8 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
             inputs_embeds = None
         B = inputs.shape[0]
         S0 = inputs_embeds.shape[1] if inputs_embeds is not None else inputs.shape[1]
+        args = GenerationArgs.from_kwargs(self, S0, kwargs)
+        max_new = args.max_new_tokens
         dev = inputs.device
         cache = KVCache(self.config, B, S0 + max_new, dev)
         cache.kmask = torch.ones((B, S0 + max_new), dtype=torch.bool, device=dev)
@@ -502,16 +504,20 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
         h_last = out.last_hidden_state[torch.arange(B, device=dev), last_idx].contiguous()
         next_pos = (position_ids.max(1).values + 1) if position_ids is not None else torch.full((B,), S0, device=dev)
         done = torch.zeros(B, dtype=torch.bool, device=dev)
+        z3 = getattr(self.get_model(), "_zero3", None)
+        check_stop = bool(args.eos_token_ids or args.stopping_criteria)
+        if args.streamer is not None:
+            args.streamer.put(torch.empty((B, 0), dtype=torch.long))     # HF streams the (here: empty) prompt ids first
         tokens = []
         for step in range(max_new):
-            logits = ops.gemm(h_last, self.lm_head.weight, out_dtype=torch.float32)
-            nxt = logits.argmax(-1)
-            nxt = torch.where(done, torch.full_like(nxt, pad), nxt)
+            logits = ops.gemm(h_last, self.lm_head.weight, out_dtype=torch.float32)             # fp32 logits (:409)
+            nxt = next_tokens(logits, args)
+            nxt = torch.where(done, torch.full_like(nxt, args.pad_token_id), nxt)
             tokens.append(nxt)
-            if eos:
-                for e in eos:
-                    done |= nxt == e
-                z3 = getattr(self.get_model(), "_zero3", None)
+            if args.streamer is not None:
+                args.streamer.put(nxt.cpu())
+            if check_stop:
+                done = should_stop(args, torch.stack(tokens, 1), logits, done)
                 if (z3.all_done(done) if z3 is not None else bool(done.all())):
                     break
             if step + 1 == max_new:
@@ -520,6 +526,8 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
                              use_cache=True)
             h_last = out.last_hidden_state[:, 0].contiguous()
             next_pos = next_pos + 1
+        if args.streamer is not None:
+            args.streamer.end()
         self.train(was_training)
         return torch.stack(tokens, 1)
 

@@ -91,6 +91,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+def gemm_set_dynamic_scheduling(on: bool) -> bool:
+    """Cluster-Launch-Control tile scheduling for the persistent GEMMs (default on); returns the previous setting."""
+    return bool(_lib.load().cb_gemm_set_dynamic_scheduling(int(on)))
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, **kw) -> torch.Tensor:
     """y = x @ weight.T + bias for x [..., K], weight [N, K] (nn.Linear)."""
     lead = x.shape[:-1]
@@ -118,11 +123,16 @@ def sva_window_attn_fwd(q, ks, vs, masks, rs, batch: int, q_side: int, need_lse:
     return out, lse
 
 
-def sva_window_attn_bwd(q, out, dout, lse, ks, vs, masks, rs, batch: int, q_side: int, windowed: bool = False):
+def sva_window_attn_bwd(q, out, dout, lse, ks, vs, masks, rs, batch: int, q_side: int, windowed: bool = False,
+                        dks=None, dvs=None):
+    """dks / dvs: optional preallocated contiguous destinations (slabs of a batched-GEMM operand)."""
     _require_cuda_bf16(q, out, dout, *ks, *vs)
     dq = torch.empty_like(q)
-    dks = [torch.empty_like(k) for k in ks]
-    dvs = [torch.empty_like(v) for v in vs]
+    dks = [torch.empty_like(k) for k in ks] if dks is None else dks
+    dvs = [torch.empty_like(v) for v in vs] if dvs is None else dvs
+    for d, k in zip(list(dks) + list(dvs), list(ks) + list(vs)):
+        if d.shape != k.shape or not d.is_contiguous():
+            raise ValueError("sva_window_attn_bwd: dk / dv destinations must be contiguous and shaped like k / v")
     mk = None
     if masks is not None:
         masks = [None if m is None else m.contiguous().view(torch.uint8) if m.dtype == torch.bool else m
@@ -135,12 +145,18 @@ def sva_window_attn_bwd(q, out, dout, lse, ks, vs, masks, rs, batch: int, q_side
     return dq, dks, dvs
 
 
-def layernorm_fwd(x, gamma, beta, eps: float = 1e-5, pos=None, side: int = 0, r: int = 0, save_stats=False):
+def layernorm_fwd(x, gamma, beta, eps: float = 1e-5, pos=None, side: int = 0, r: int = 0, save_stats=False, out=None):
+    """out: optional preallocated contiguous [rows, C] bf16 destination (e.g. one slab of a batched-GEMM operand)."""
     _require_cuda_bf16(x, gamma, beta, pos)
     C_ = x.shape[-1]
     x2 = x.reshape(-1, C_)
     rows = x2.shape[0]
-    y = torch.empty_like(x2)
+    if out is not None:
+        if out.shape != x2.shape or not out.is_contiguous() or out.dtype != torch.bfloat16:
+            raise ValueError("layernorm_fwd: `out` must be a contiguous bf16 [rows, C] tensor")
+        y = out
+    else:
+        y = torch.empty_like(x2)
     mean = rstd = None
     if save_stats:
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)

@@ -211,6 +211,10 @@ int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, 
 int cb_adamw_ex(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
                 float eps, float weight_decay, int step, float grad_scale, const float* clip_coef, int background,
                 void* stream);
+/* GEMM tile scheduling: 1 (default; env CB_GEMM_CLC=0 to start with 0) = one CTA / CTA pair per tile in the grid, tiles
+ * handed out by Cluster Launch Control so the GEMM tolerates SMs held by collectives / the background optimizer;
+ * 0 = static persistent walk.  Returns the previous setting.  Results are bit-identical either way. */
+int cb_gemm_set_dynamic_scheduling(int on);
 /* acc[0] += sum of squares of n bf16 values (deterministic two-stage reduction; workspace >= grid floats, 4096 suffices) */
 int cb_sumsq_bf16(const void* g, int64_t n, float* acc, float* workspace, int64_t workspace_floats, int background,
                   void* stream);

@@ -426,3 +426,44 @@ def test_valid_label_ranges_cover_exactly_the_valid_shifted_labels():
             mask[a:b] = True
         assert torch.equal(mask, (shift != -100).view(-1)) and n == int(mask.sum())
         assert all(ranges[i][1] < ranges[i + 1][0] for i in range(len(ranges) - 1))       # maximal, ordered runs
+
+
+# ------------------------------------------------------------------------------------------------ generate() policy (A12)
+def test_sampling_warpers_match_transformers():
+    """temperature / top-k / top-p filtering == HF's LogitsWarpers (what GenerationMixin.generate applies for the
+    reference's callers: model_worker.py:177-187 passes do_sample, temperature, top_p)."""
+    from transformers.generation.logits_process import TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper
+    from cambrian_b200.generation import warp_logits
+    torch.manual_seed(0)
+    logits = torch.randn(3, 500) * 3
+    for temp, k, p in [(0.7, 50, 0.9), (1.0, 0, 0.5), (1.3, 10, 1.0), (0.2, 50, 0.95)]:
+        want = logits.clone()
+        if temp != 1.0:
+            want = TemperatureLogitsWarper(temp)(None, want)
+        if k:
+            want = TopKLogitsWarper(k)(None, want)
+        if p < 1.0:
+            want = TopPLogitsWarper(p)(None, want)
+        got = warp_logits(logits, temp, k, p)
+        assert torch.equal(torch.isinf(got), torch.isinf(want)), (temp, k, p)
+        keep = ~torch.isinf(want)
+        torch.testing.assert_close(got[keep], want[keep])
+
+
+def test_generation_kwargs_are_honoured_or_rejected_never_dropped():
+    from cambrian_b200.generation import GenerationArgs
+    model = ns(config=ns(eos_token_id=2, pad_token_id=None), generation_config=None)
+    a = GenerationArgs.from_kwargs(model, 10, dict(do_sample=True, temperature=0.2, top_p=0.7, max_new_tokens=7, num_beams=1,
+                                                   use_cache=True, stopping_criteria=[lambda i, s: False], streamer=None))
+    assert (a.do_sample, a.temperature, a.top_p, a.top_k, a.max_new_tokens, a.eos_token_ids, a.pad_token_id) == \
+        (True, 0.2, 0.7, 50, 7, [2], 2) and len(a.stopping_criteria) == 1
+    a = GenerationArgs.from_kwargs(model, 10, dict(do_sample=False, temperature=0, max_length=30))     # inference.py:77-85
+    assert not a.do_sample and a.max_new_tokens == 20
+    with pytest.raises(NotImplementedError, match="num_beams"):
+        GenerationArgs.from_kwargs(model, 10, dict(num_beams=4))
+    with pytest.raises(NotImplementedError, match="repetition_penalty"):
+        GenerationArgs.from_kwargs(model, 10, dict(repetition_penalty=1.2))
+    with pytest.raises(TypeError, match="frobnicate"):
+        GenerationArgs.from_kwargs(model, 10, dict(frobnicate=1))
+    with pytest.raises(ValueError, match="top_p"):
+        GenerationArgs.from_kwargs(model, 10, dict(do_sample=True, top_p=0.0))

@@ -33,6 +33,10 @@ def test_gemm_epilogues(capsys):
     _run("probe1", "gemm_epi", capsys, 10)
 
 
+def test_gemm_dynamic_scheduling_is_bit_identical(capsys):
+    _run("probe1", "gemm_clc", capsys, 12)
+
+
 def test_gemm_cta_pair_kernel(capsys):
     _run("probe1", "gemm_2cta", capsys, 24)
 

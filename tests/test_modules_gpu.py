@@ -499,3 +499,56 @@ def test_fused_loss_with_label_ranges_matches_full_rows():
     assert res[0][1].keys() == res[1][1].keys()
     for k in res[0][1]:
         assert rel_err(res[1][1][k], res[0][1][k]) < 2e-2, k
+
+
+def test_generate_sampling_stopping_criteria_and_streamer():
+    """A12: the keywords the reference's callers pass (model_worker.py:177-187: do_sample, temperature, top_p,
+    max_new_tokens, streamer, stopping_criteria, use_cache; inference.py:77-85: num_beams=1) are honoured."""
+    cfg = tiny_cambrian_config()
+    model = _build_tiny_model(cfg).eval()
+    ids, attn, images = _dynamic_batch(cfg, B=2, L=24)
+    imgs = [i.to(dev).bfloat16() for i in images]
+    common = dict(images=imgs, image_sizes=[(336, 336)] * 2, attention_mask=attn.to(dev))
+
+    class Streamer:
+        def __init__(self):
+            self.chunks, self.ended = [], False
+
+        def put(self, t):
+            self.chunks.append(t.clone())
+
+        def end(self):
+            self.ended = True
+
+    greedy = model.generate(ids.to(dev), max_new_tokens=6, do_sample=False, temperature=0, num_beams=1, use_cache=True, **common)
+    # seeded sampling is reproducible, differs from greedy somewhere, and stays inside the top-k set
+    gens = []
+    for _ in range(2):
+        g = torch.Generator(device=dev).manual_seed(123)
+        gens.append(model.generate(ids.to(dev), max_new_tokens=6, do_sample=True, temperature=1.5, top_p=0.9, generator=g, **common))
+    assert torch.equal(gens[0], gens[1]) and gens[0].shape == (2, 6)
+    # temperature -> 0 sampling collapses to greedy
+    g = torch.Generator(device=dev).manual_seed(5)
+    cold = model.generate(ids.to(dev), max_new_tokens=6, do_sample=True, temperature=1e-4, top_k=0, generator=g, **common)
+    assert torch.equal(cold, greedy)
+    # stopping criteria (HF signature: (generated_ids, scores) -> bool / [B] bool) and streamer
+    st = Streamer()
+    seen = []
+
+    def stop_after_three(gen_ids, scores):
+        seen.append(tuple(gen_ids.shape))
+        return gen_ids.shape[1] >= 3
+    out = model.generate(ids.to(dev), max_new_tokens=6, stopping_criteria=[stop_after_three], streamer=st, **common)
+    assert out.shape == (2, 3) and torch.equal(out, greedy[:, :3])
+    assert seen == [(2, 1), (2, 2), (2, 3)]
+    assert st.ended and st.chunks[0].shape == (2, 0) and torch.equal(torch.stack(st.chunks[1:], 1), out.cpu())
+    # EOS: the sequence that emits it is padded afterwards, the other one keeps going
+    eos = int(greedy[0, 1])
+    out = model.generate(ids.to(dev), max_new_tokens=6, eos_token_id=eos, pad_token_id=0, **common)
+    row = out[0].tolist()
+    k = row.index(eos)
+    assert all(t == 0 for t in row[k + 1:])
+    with pytest.raises(NotImplementedError):
+        model.generate(ids.to(dev), max_new_tokens=2, num_beams=3, **common)
+    with pytest.raises(TypeError):
+        model.generate(ids.to(dev), max_new_tokens=2, not_a_generate_kwarg=True, **common)

@@ -157,6 +157,61 @@ def group_gemm_swiglu():
           f"unfused {t_u:.4f} ms", flush=True)
 
 
+def group_gemm_clc():
+    """Cluster-Launch-Control tile scheduling vs the static persistent walk: bit-identical outputs for every kernel variant
+    (single CTA BN 64/128/256, CTA pair, every operand major, batched, accumulate, fused SwiGLU), alone and while another
+    stream keeps the SMs busy (the situation it exists for); then the timing of both."""
+    cases = [  # M, N, K, a_mn, b_mn, force_bn, batch
+        (4096, 4096, 512, False, False, 64, 0), (4096, 4096, 1024, False, False, 128, 0), (8192, 4096, 512, False, False, 256, 0),
+        (8192, 8192, 1024, False, False, 512, 0), (4096, 4096, 2048, False, True, 512, 0), (4096, 4096, 2048, True, True, 512, 0),
+        (4096, 4096, 2048, True, False, 128, 0), (2048, 1024, 256, False, False, 64, 6), (8200, 4104, 264, False, False, 0, 0),
+        (4096, 1024, 8192, True, True, 0, 0), (8192, 14336, 4096, False, True, 0, 0)]
+    hog_a = torch.randn(64 << 20, device=dev)
+    side = torch.cuda.Stream()
+    for (M, N, K, a_mn, b_mn, bn, batch) in cases:
+        bs = (batch,) if batch else ()
+        a = torch.randn(*bs, *((K, M) if a_mn else (M, K)), device=dev).bfloat16()
+        b = torch.randn(*bs, *((K, N) if b_mn else (N, K)), device=dev).bfloat16()
+        acc0 = torch.randn(*bs, M, N, device=dev).bfloat16()
+        outs = []
+        for mode in (0, 1, 2):                 # static, CLC, CLC under contention
+            ops.gemm_set_dynamic_scheduling(mode > 0)
+            if mode == 2:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(6):
+                        hog_a.mul_(1.0001)     # 256 MB elementwise passes: every SM's thread slots taken in bursts
+            o1 = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, force_bn=bn)
+            o2 = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, force_bn=bn, out=acc0.clone(), accumulate=True)
+            o3 = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, force_bn=bn, out_dtype=torch.float32)
+            torch.cuda.synchronize()
+            outs.append((o1, o2, o3))
+        same = all(torch.equal(x, y) for m in (1, 2) for x, y in zip(outs[0], outs[m]))
+        A = a.float().transpose(-1, -2) if a_mn else a.float()
+        B = b.float() if b_mn else b.float().transpose(-1, -2)
+        e = rel_err(outs[1][2], A @ B)
+        print(f"clc M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} bn={bn} batch={batch}: identical={same} fp32 err {e:.2e}"
+              f" {'OK' if same and e < 2e-5 else 'FAIL'}")
+    x = torch.randn(8192, 4096, device=dev).bfloat16()
+    w = torch.randn(2 * 14336, 4096, device=dev).bfloat16() * 0.02
+    res = []
+    for mode in (0, 1):
+        ops.gemm_set_dynamic_scheduling(bool(mode))
+        res.append(ops.gemm_swiglu(x, w))
+        torch.cuda.synchronize()
+    same = torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    print(f"clc fused gate/up + SwiGLU M=8192 F=14336 K=4096: identical={same} {'OK' if same else 'FAIL'}")
+    for (M, N, K) in ((8192, 28672, 4096), (8192, 4096, 14336), (8192, 6144, 4096), (4096, 1024, 1024), (2304, 1024, 1024)):
+        a = torch.randn(M, K, device=dev).bfloat16()
+        b = torch.randn(N, K, device=dev).bfloat16()
+        t = []
+        for mode in (0, 1):
+            ops.gemm_set_dynamic_scheduling(bool(mode))
+            t.append(timeit(lambda: ops.gemm(a, b)))
+        print(f"clc timing M={M} N={N} K={K}: static {2 * M * N * K / t[0] / 1e9:7.0f} TF/s  dynamic {2 * M * N * K / t[1] / 1e9:7.0f} TF/s")
+    ops.gemm_set_dynamic_scheduling(True)
+
+
 def group_gemm_perf():
     for (M, N, K) in [(8192, 8192, 8192), (8192, 14336, 4096), (8192, 4096, 14336), (4096, 4096, 4096),
                       (2304, 1024, 1024)]:
