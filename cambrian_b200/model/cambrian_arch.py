@@ -30,6 +30,7 @@ from .vision_sampler import VisionTokenSampler
 
 IGNORE_INDEX = -100
 IMAGE_TOKEN_INDEX = -200
+_TOWER_STREAMS = __import__("os").environ.get("CB_TOWER_STREAMS", "1") != "0"
 
 
 def _kv_sizes(aux_token_lens, query_num):
@@ -175,8 +176,36 @@ class CambrianMetaForCausalLM(ABC):
         return self.get_model().get_vision_tower_aux_list()
 
     def encode_images(self, image_aux_list):
-        """cambrian_arch.py:332-338."""
-        return [tower(img) for img, tower in zip(image_aux_list, self.get_model().get_vision_tower_aux_list())]
+        """cambrian_arch.py:332-338.  The towers are independent of each other (and frozen in every released recipe), so
+        each runs on its own CUDA stream: most ViT GEMMs are a wave and a bit on 148 SMs (M = B * 577 rows -> 152 tiles),
+        and with one-CTA-per-tile grids the idle SMs of one tower's last wave take tiles of another tower's kernel instead
+        of waiting (CB_TOWER_STREAMS=0 runs them back to back on the current stream)."""
+        towers = self.get_model().get_vision_tower_aux_list()
+        imgs = list(image_aux_list)
+        multi = (_TOWER_STREAMS and len(towers) > 1 and all(torch.is_tensor(i) and i.is_cuda for i in imgs)
+                 and not any(getattr(t, "unfreeze_mm_vision_tower", False) for t in towers))
+        if not multi:
+            return [tower(img) for img, tower in zip(imgs, towers)]
+        main = torch.cuda.current_stream()
+        pool = getattr(self, "_tower_streams", None)
+        if pool is None or len(pool) < len(towers) or pool[0].device != imgs[0].device:
+            pool = [torch.cuda.Stream(device=imgs[0].device) for _ in towers]
+            self._tower_streams = pool
+        # the largest tower first: its big GEMMs are the backdrop the small ones fill into
+        order = sorted(range(len(towers)), key=lambda i: -imgs[i].shape[-1])
+        outs = [None] * len(towers)
+        for i in order:
+            st = pool[i]
+            st.wait_stream(main)                      # inputs (H2D copies, casts) were produced on the current stream
+            with torch.cuda.stream(st):
+                outs[i] = towers[i](imgs[i])
+        for i in order:
+            main.wait_stream(pool[i])
+            if torch.is_tensor(outs[i]):
+                outs[i].record_stream(main)           # allocated on the side stream, consumed (and freed) on the main one
+            if torch.is_tensor(imgs[i]):
+                imgs[i].record_stream(pool[i])
+        return outs
 
     def rearrange_vision_tower_features_train(self, vision_tower_aux_feature_list, vision_tower_aux_attention_masks_list,
                                               query_side_len):

@@ -552,3 +552,24 @@ def test_generate_sampling_stopping_criteria_and_streamer():
         model.generate(ids.to(dev), max_new_tokens=2, num_beams=3, **common)
     with pytest.raises(TypeError):
         model.generate(ids.to(dev), max_new_tokens=2, not_a_generate_kwarg=True, **common)
+
+
+def test_towers_on_separate_streams_give_identical_features():
+    """encode_images (cambrian_arch.py:332-338) runs each frozen tower on its own stream; the features must be the ones the
+    sequential schedule produces, bit for bit, call after call."""
+    import cambrian_b200.model.cambrian_arch as A
+    cfg = tiny_cambrian_config()
+    model = _build_tiny_model(cfg).eval()
+    _, _, _, _, images, _ = _tiny_batch(cfg)
+    imgs = [i.to(dev).bfloat16() for i in images]
+    old = A._TOWER_STREAMS
+    try:
+        A._TOWER_STREAMS = False
+        seq = model.encode_images(imgs)
+        A._TOWER_STREAMS = True
+        for _ in range(3):
+            par = model.encode_images(imgs)
+            torch.cuda.synchronize()
+            assert all(torch.equal(a, b) for a, b in zip(seq, par))
+    finally:
+        A._TOWER_STREAMS = old
