@@ -16,6 +16,18 @@ import torch
 from . import ops
 
 
+def _ranged(tag):
+    """NVTX range around a Function's forward / backward (ops.nvtx: a no-op unless CB_NVTX=1)."""
+    def deco(fn):
+        def wrapped(*a, **k):
+            with ops.nvtx(tag):
+                return fn(*a, **k)
+        wrapped.__name__ = fn.__name__
+        wrapped.__doc__ = fn.__doc__
+        return wrapped
+    return deco
+
+
 def _notify(param):
     """Tell the TrainEngine (if any) that one gradient contribution of `param` has been enqueued on the stream; it uses
     the per-step contribution counts to launch a bucket's all-reduce as soon as the bucket is final."""
@@ -228,6 +240,8 @@ class MeanTokensFn(torch.autograd.Function):
 # SVA layer (VisionCrossAttentionLayer.forward, vision_sampler.py:270-327)
 # ------------------------------------------------------------------------------------------------------------------
 class SVALayerFn(torch.autograd.Function):
+    _nvtx = "SVALayer"
+
     """args: meta, queries [N,Dq], ctx [N,Dc], feats_0..T-1, then the layer's parameters in `meta['names']` order.
 
     meta = dict(T, rs, masks (list of bool tensors or None), natural=(B, q_side) or None (window-rearranged inputs),
@@ -235,6 +249,7 @@ class SVALayerFn(torch.autograd.Function):
     """
 
     @staticmethod
+    @_ranged("sva_layer.fwd")
     def forward(ctx, meta, queries, ctxf, *tensors):
         T, rs = meta["T"], meta["rs"]
         _await(*meta["params"])
@@ -298,6 +313,7 @@ class SVALayerFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_ranged("sva_layer.bwd")
     def backward(ctx, dout):
         meta = ctx.meta
         T, rs, masks = meta["T"], meta["rs"], meta["masks"]
@@ -418,6 +434,8 @@ def _slice_b(D):
 # LLaMA decoder layer (HF LlamaDecoderLayer as called from cambrian_llama.py:142-166)
 # ------------------------------------------------------------------------------------------------------------------
 class DecoderLayerFn(torch.autograd.Function):
+    _nvtx = "DecoderLayer"
+
     """x [B,S,H] -> x'.  Parameters: input_ln, qkv_w (fused [ (nh+2nkv)*hd, H ]), o_w, post_ln, gu_w (fused [2I, H]), down_w.
 
     meta = dict(nh, nkv, hd, eps, hf_cast, cos, sin, pos (int64 [B*S]), kmask (bool [B,S] or None), params (6 Parameters),
@@ -447,6 +465,7 @@ class DecoderLayerFn(torch.autograd.Function):
         return out.view(B, S, H), None
 
     @staticmethod
+    @_ranged("decoder_layer.fwd")
     def forward(ctx, meta, x, ln1, q_w, k_w, v_w, o_w, ln2, gate_w, up_w, down_w):
         # q_w/k_w/v_w and gate_w/up_w are the HF-named leaf parameters (for autograd bookkeeping); the GEMMs use the
         # fused views meta["qkv_w"] / meta["gu_w"] over the same storage (CBLlamaDecoderLayer._fused()).
@@ -462,6 +481,7 @@ class DecoderLayerFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_ranged("decoder_layer.bwd")
     def backward(ctx, dout):
         meta = ctx.meta
         sv = ctx.saved_tensors
@@ -561,11 +581,14 @@ class EmbedSpliceFn(torch.autograd.Function):
 
 
 class LMHeadLossFn(torch.autograd.Function):
+    _nvtx = "LMHeadLoss"
+
     """cambrian_llama.py:402-422: lm_head -> logits.float() -> shift -> CrossEntropyLoss(mean over non-ignored), computed
     in row chunks so the [B*S, V] logits are never resident at once; the backward GEMMs run inside the forward (the
     per-chunk (softmax - onehot) overwrites the chunk's logits), so the only saved tensor is dhidden."""
 
     @staticmethod
+    @_ranged("lm_head_loss.fwd")
     def forward(ctx, meta, hidden, weight):
         labels = meta["shift_labels"]  # int64 [B*S]: labels[b, s+1] at row (b, s), -100 on the last position
         rows, H = hidden.reshape(-1, hidden.shape[-1]).shape
@@ -640,6 +663,7 @@ class LMHeadLossFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @_ranged("lm_head_loss.bwd")
     def backward(ctx, dloss):
         dh = ctx.saved_tensors[0]
         if ctx.has_dw:      # plain-autograd path (no TrainEngine): honour an upstream scale, e.g. (loss / accum).backward()
@@ -683,6 +707,22 @@ class SpanMergeFn(torch.autograd.Function):
     def backward(ctx, dout):
         dout = dout.contiguous()
         return dout, ops.span_gather(dout, ctx.start, ctx.q_side), None, None
+
+
+class ResizeTokenGridFn(torch.autograd.Function):
+    """cambrian_arch.py:394-401: a query group whose side differs from the final grid is resized with fp32 bilinear
+    interpolation (align_corners=False): [B, q*q, C] -> [B, f*f, C].  Forward only: no released Cambrian-1 recipe uses more
+    than one query group (finetune_cambrian_{8b,13b,34b}.sh: num_query_group 1, query_num_list [576]), so the adjoint
+    kernel has not been written; training through it raises."""
+
+    @staticmethod
+    def forward(ctx, x, q_side, f_side):
+        return ops.bilinear(x.contiguous(), q_side, q_side, f_side, f_side)
+
+    @staticmethod
+    def backward(ctx, dy):
+        raise NotImplementedError("backward of the query-grid resize (cambrian_arch.py:394-401) is not implemented: "
+                                  "query groups whose side differs from the final grid are inference-only")
 
 
 class ExpandRowsFn(torch.autograd.Function):

@@ -307,11 +307,12 @@ class TrainEngine:
                 ev.record(st)
                 self._ready[b] = ev
 
-        if st is not None:
-            with torch.cuda.stream(st):
+        with ops.nvtx(f"optimizer.bucket{b}"):
+            if st is not None:
+                with torch.cuda.stream(st):
+                    run()
+            else:
                 run()
-        else:
-            run()
 
     def _adamw(self, master, m, v, g, p16, lr, wd, step, coef):
         ops.adamw(master, m, v, g, p16, lr, self.betas[0], self.betas[1], self.eps, wd, step,

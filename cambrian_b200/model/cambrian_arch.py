@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..autograd import EmbedSpliceFn, ExpandRowsFn, MeanTokensFn, _await
+from ..autograd import EmbedSpliceFn, ExpandRowsFn, MeanTokensFn, ResizeTokenGridFn, _await
 from .multimodal_encoder.builder import build_vision_tower_aux_list
 from .multimodal_projector.builder import CBGELU, CBLayerNorm, CBLinear, build_vision_projector
 from .vision_sampler import VisionTokenSampler
@@ -263,10 +263,10 @@ class CambrianMetaForCausalLM(ABC):
                 ctx_g = ExpandRowsFn.apply(ctx, query_num)
                 f_i, m_i = self.rearrange_vision_tower_features_inference(aux, qs, image_sizes)     # :389
                 qf = getattr(model, f"vision_sampler_{g}")(queries.view(n, 1, -1), ctx_g.view(n, 1, -1), *f_i, *m_i)
-                if qs != fh:
-                    raise NotImplementedError("query groups with a side different from the final grid "
-                                              "(cambrian_arch.py:394-401)")
-                outs.append(qf.view(bs, query_num, -1))
+                qf = qf.view(bs, query_num, -1)
+                if qs != fh:                                                                       # :394-401
+                    qf = ResizeTokenGridFn.apply(qf, qs, fh)
+                outs.append(qf)
             image_features = outs[0] if len(outs) == 1 else torch.cat(outs, -1)
             feats_final, masks_final = self.rearrange_vision_tower_features_inference(aux, fh, image_sizes, unpad=True)
         else:
@@ -415,10 +415,10 @@ class CambrianMetaForCausalLM(ABC):
                 masks = _masks_for(image_aux_attention_masks_list, aux, qs, n)
                 sampler = getattr(model, f"vision_sampler_{g}")
                 qf = sampler(queries.view(n, 1, -1), ctx_g.view(n, 1, -1), *aux, *masks, natural_layout=(bs, qs))
-                if qs != q_side:
-                    raise NotImplementedError("query groups with a side different from the final grid "
-                                              "(bilinear resize of the query grid, cambrian_arch.py:394-401)")
-                outs.append(qf.view(bs, query_num, -1))
+                qf = qf.view(bs, query_num, -1)
+                if qs != q_side:                                                                     # :394-401
+                    qf = ResizeTokenGridFn.apply(qf, qs, q_side)
+                outs.append(qf)
             image_features = outs[0] if len(outs) == 1 else torch.cat(outs, -1)
             feats_final = aux                                                                    # natural layout
             masks_final = _masks_for(image_aux_attention_masks_list, aux, q_side, bs * q_num)

@@ -109,7 +109,8 @@ class BaseVisionTower(nn.Module):
             raise RuntimeError(f"{type(self).__name__}: call load_model() first")
         if not images.is_cuda:
             raise RuntimeError("cambrian_b200 towers need CUDA inputs (no CPU fallback)")
-        return self._run(images.to(device=self.device, dtype=torch.bfloat16)).to(images.dtype)
+        with ops.nvtx(f"tower.{type(self).__name__}"):
+            return self._run(images.to(device=self.device, dtype=torch.bfloat16)).to(images.dtype)
 
     @property
     def dummy_feature(self):

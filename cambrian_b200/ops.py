@@ -16,6 +16,40 @@ ACT = {None: 0, "none": 0, "gelu": 1, "gelu_erf": 1, "gelu_tanh": 2, "gelu_pytor
 
 _ws_cache: dict = {}
 
+# NVTX ranges around every block of the hot path (decoder layer fwd / bwd, SVA layer fwd / bwd, each tower, fused loss,
+# optimizer): CB_NVTX=1 turns them on for nsys / ncu --nvtx captures; off, `nvtx()` is a shared no-op context.
+_NVTX = os.environ.get("CB_NVTX", "0") != "0"
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _Null()
+
+
+class _Range:
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *a):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
+def nvtx(name: str):
+    return _Range(name) if _NVTX else _NULL
+
 
 def _require_cuda_bf16(*ts):
     for t in ts:

@@ -149,9 +149,21 @@ def connector(sd, cfg, tower_feats, aux_masks):
     aux = [mm_projector_aux(sd, f"model.mm_projector_aux_{i}.", f) for i, f in enumerate(tower_feats)]
     ctx = aux[0].mean(1).view(B, 1, 1, -1)                                   # :377
     feats_w = [window_rearrange(a, q_side) for a in aux]
-    queries = sd["model.vision_query"][0].view(1, 1, 1, -1).expand(B, q_num, -1, -1).flatten(0, 1)
     ctx_q = ctx.expand(-1, q_num, 1, -1).flatten(0, 1)
-    qf = sva_sampler(sd, "model.vision_sampler_0.", queries, ctx_q, feats_w, aux_masks, cfg["connector_depth"])
+    groups = []
+    for g, qn in enumerate(cfg.get("query_num_list", [q_num])):              # :382-402, one sampler per query group
+        qs = int(qn ** 0.5)
+        queries = sd["model.vision_query"][g].view(1, 1, 1, -1).expand(B, qn, -1, -1).flatten(0, 1)
+        ctx_g = ctx.expand(-1, qn, 1, -1).flatten(0, 1)
+        fw = feats_w if qs == q_side else [window_rearrange(a, qs) for a in aux]
+        gm = aux_masks if qs == q_side else cfg.get("group_masks", {}).get(g)
+        qf = sva_sampler(sd, f"model.vision_sampler_{g}.", queries, ctx_g, fw, gm, cfg["connector_depth"]).view(B, qn, -1)
+        if qs != q_side:                                                     # :394-401 bilinear resize of the query grid
+            t = qf.permute(0, 2, 1).contiguous().view(B, -1, qs, qs)
+            t = F.interpolate(t.float(), size=(q_side, q_side), mode="bilinear", align_corners=False).to(qf.dtype)
+            qf = t.permute(0, 2, 3, 1).contiguous().flatten(1, 2)
+        groups.append(qf)
+    qf = torch.cat(groups, -1)
     img = mlp2x_gelu(sd, "model.mm_projector.", qf.view(B, q_num, -1))       # :410-411
     img = img.view(B, q_side, q_side, -1)
     nl = sd["model.image_newline"][None, None, None, :].expand(B, q_side, 1, -1)

@@ -174,7 +174,8 @@ def oracle_cfg(cfg):
                 connector_depth=cfg.connector_depth, connector_only=cfg.connector_only,
                 num_of_vision_sampler_layers=cfg.num_of_vision_sampler_layers,
                 start_of_vision_sampler_layers=cfg.start_of_vision_sampler_layers,
-                stride_of_vision_sampler_layers=cfg.stride_of_vision_sampler_layers, image_position=cfg.image_position)
+                stride_of_vision_sampler_layers=cfg.stride_of_vision_sampler_layers, image_position=cfg.image_position,
+                query_num_list=list(getattr(cfg, "query_num_list", [cfg.image_token_len])))
 
 
 def rope_theta(cfg):

@@ -413,3 +413,43 @@ def test_greedy_generate_token_exact_32_tokens():
     assert got == t_32, f"CUDA greedy != fp32 oracle greedy:\n{got}\n{t_32}\nmargins {m_32}"
     assert len(set(got)) >= 8, f"degenerate decode: {got}"
     assert min(m_32) > 2.0, f"test model lost its margin (min {min(m_32)}): re-calibrate"
+
+
+def test_two_query_groups_with_grid_resize_match_oracle():
+    """cambrian_arch.py:382-402 with num_query_group = 2: a 4x4 and a 2x2 query group, each with its own sampler and kv
+    window sizes; the 2x2 group's output is bilinearly resized to the final 4x4 grid (:394-401) and channel-concatenated
+    before mm_projector.  Inference (the resize has no backward here)."""
+    from test_modules_gpu import _build_tiny_model, _tiny_batch, _tower_fn, TOWER_KINDS
+    from oracle import cambrian_oracle as O
+    cfg = tiny_cambrian_config()
+    cfg.num_query_group = 2
+    cfg.query_num_list = [16, 4]
+    model = _build_tiny_model(cfg).eval()
+    assert hasattr(model.get_model(), "vision_sampler_1") and model.get_model().vision_query.shape[0] == 2
+    assert model.get_model().mm_projector[0].weight.shape[1] == 2 * 1024
+    ids, labels, attn, pos, images, _ = _tiny_batch(cfg)
+    towers = model.get_model().vision_tower_aux_list
+    sd = sd_cpu32(model)
+    names = list(sd.keys())
+    for i, t in enumerate(towers):
+        sd.update({f"tower{i}." + k: v for k, v in sd_cpu32(t.vision_tower).items()})
+    fns = [_tower_fn(kind, t) for kind, t in zip(TOWER_KINDS, towers)]
+    ocfg = oracle_cfg(cfg)
+
+    def run(s, ii, aa, pp, *ims):
+        feats = []
+        for i, (f, im) in enumerate(zip(fns, ims)):
+            o = f({k[len(f"tower{i}."):]: v for k, v in s.items() if k.startswith(f"tower{i}.")}, im)
+            feats.append(o.to(torch.bfloat16).to(o.dtype))
+        img, feats_w, ctx_q = O.connector(s, ocfg, feats, None)
+        hid = O.decoder(s, ocfg, O.splice(s, ii, img), pp, aa, feats_w, None, ctx_q)
+        return O.lm_loss(s, hid, None)[0]
+
+    with torch.no_grad():
+        ref, eag = both_modes(run, sd, ids, attn, pos, *[bf(i) for i in images])
+        out = model(input_ids=ids.to(dev), attention_mask=attn.to(dev), position_ids=pos.to(dev),
+                    images=[i.to(dev).bfloat16() for i in images])
+    valid = attn.to(dev)
+    pc = ParityCollector()
+    pc.check(out.logits[valid], ref[valid], eag[valid], "two query groups (16 + 4 -> resize): logits")
+    pc.done()
