@@ -346,11 +346,11 @@ class SVALayerFn(torch.autograd.Function):
         stacks = {}
         dKs, dVs = [None] * T, [None] * T
         for grp in groups:
-            g = len(grp)
-            wstack = _uniform_stack([P[f"{kv}_w_{i}"] for i in grp for kv in ("k", "v")]) if g > 1 else None
+            ng = len(grp)
+            wstack = _uniform_stack([P[f"{kv}_w_{i}"] for i in grp for kv in ("k", "v")]) if ng > 1 else None
             xstack = _uniform_stack([t for i in grp for t in (kins[i], vins[i])]) if wstack is not None else None
             if wstack is not None and xstack is not None:
-                dkv = torch.empty((2 * g,) + tuple(Ks[grp[0]].shape), dtype=torch.bfloat16, device=dout.device)
+                dkv = torch.empty((2 * ng,) + tuple(Ks[grp[0]].shape), dtype=torch.bfloat16, device=dout.device)
                 for j, i in enumerate(grp):
                     dKs[i], dVs[i] = dkv[2 * j], dkv[2 * j + 1]
                 stacks[grp[0]] = (wstack, xstack, dkv)

@@ -46,6 +46,19 @@ def _round_up(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
+def cosine_schedule_with_warmup(num_warmup_steps: int, num_training_steps: int, num_cycles: float = 0.5):
+    """`lr_lambda` equal to transformers.get_cosine_schedule_with_warmup (the reference scripts train with
+    `--lr_scheduler_type cosine --warmup_ratio 0.03`, scripts/cambrian/finetune_cambrian_8b.sh): step -> multiplier."""
+    import math
+
+    def f(step: int) -> float:
+        if step < num_warmup_steps:
+            return float(step) / float(max(1, num_warmup_steps))
+        progress = float(step - num_warmup_steps) / float(max(1, num_training_steps - num_warmup_steps))
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress)))
+    return f
+
+
 class TrainEngine:
     def __init__(self, model: torch.nn.Module, lr: float = 4e-5, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, bucket_mb: float = 256.0, process_group=None, overlap: bool = True,

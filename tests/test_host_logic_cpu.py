@@ -467,3 +467,16 @@ def test_generation_kwargs_are_honoured_or_rejected_never_dropped():
         GenerationArgs.from_kwargs(model, 10, dict(frobnicate=1))
     with pytest.raises(ValueError, match="top_p"):
         GenerationArgs.from_kwargs(model, 10, dict(do_sample=True, top_p=0.0))
+
+
+def test_cosine_schedule_equals_transformers():
+    from transformers import get_cosine_schedule_with_warmup
+    from cambrian_b200.engine import cosine_schedule_with_warmup
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=1.0)
+    sched = get_cosine_schedule_with_warmup(opt, 7, 100)
+    f = cosine_schedule_with_warmup(7, 100)
+    for step in range(100):
+        assert abs(sched.get_last_lr()[0] - f(step)) < 1e-12, step
+        opt.step()
+        sched.step()
