@@ -30,6 +30,9 @@ from ...autograd import DecoderLayerFn, LinearFn, LMHeadLossFn, RMSNormFn, SpanM
 from ..cambrian_arch import IGNORE_INDEX, CambrianMetaForCausalLM, CambrianMetaModel, WindowedFeatures
 
 
+_DECODE_GRAPH = __import__("os").environ.get("CB_DECODE_GRAPH", "1") != "0"
+
+
 class CambrianConfig(LlamaConfig):
     model_type = "cambrian_llama"
 
@@ -186,12 +189,19 @@ class CBLlamaDecoderLayer(nn.Module):
         h = ops.rmsnorm_fwd(x2, self.input_layernorm.weight, self.input_layernorm.variance_epsilon, rt["hf_cast"])
         qkv = ops.gemm(h, qkv_w)
         ops.rope_(qkv, rt["pos"], rt["cos"], rt["sin"], nh + nkv, hd)
-        t0 = cache.length
         kc, vc = cache.k[self.layer_idx], cache.v[self.layer_idx]
-        kc[:, t0:t0 + S].copy_(qkv[:, nh * hd:(nh + nkv) * hd].view(B, S, nkv, hd))   # cache append (memory plumbing)
-        vc[:, t0:t0 + S].copy_(qkv[:, (nh + nkv) * hd:].view(B, S, nkv, hd))
         q = qkv[:, : nh * hd].view(B, S, nh, hd)
-        attn = ops.attn_fwd(q, kc[:, : t0 + S], vc[:, : t0 + S], causal=True, kmask=rt["kmask"])
+        if cache.slot is not None:
+            # static-shape decode step (CUDA-graph replay): the write slot is a DEVICE index, attention runs over the whole
+            # cache buffer and the validity mask (updated on the device) hides the slots not written yet
+            kc.index_copy_(1, cache.slot, qkv[:, nh * hd:(nh + nkv) * hd].view(B, S, nkv, hd))
+            vc.index_copy_(1, cache.slot, qkv[:, (nh + nkv) * hd:].view(B, S, nkv, hd))
+            attn = ops.attn_fwd(q, kc, vc, causal=False, kmask=rt["kmask"])
+        else:
+            t0 = cache.length
+            kc[:, t0:t0 + S].copy_(qkv[:, nh * hd:(nh + nkv) * hd].view(B, S, nkv, hd))   # cache append (memory plumbing)
+            vc[:, t0:t0 + S].copy_(qkv[:, (nh + nkv) * hd:].view(B, S, nkv, hd))
+            attn = ops.attn_fwd(q, kc[:, : t0 + S], vc[:, : t0 + S], causal=True, kmask=rt["kmask"])
         x1 = ops.gemm(attn.view(rows, nh * hd), a.o_proj.weight, residual=x2)
         h2 = ops.rmsnorm_fwd(x1, self.post_attention_layernorm.weight, self.post_attention_layernorm.variance_epsilon,
                              rt["hf_cast"])
@@ -211,6 +221,7 @@ class KVCache:
         self.length = 0
         self.max_len = max_len
         self.kmask = None  # [B, max_len] bool, key validity over the whole cache
+        self.slot = None   # device int64 [1]: write position of a static-shape (graph-replayed) decode step
 
     def get_seq_length(self):
         return self.length
@@ -297,7 +308,9 @@ class CambrianLlamaModel(CambrianMetaModel, CBLlamaModel):
         cos, sin = self._rope_tables(dev)
         kmask = None
         if cache is not None:
-            if cache.kmask is not None:
+            if cache.slot is not None:
+                kmask = cache.kmask                      # whole buffer; the mask itself is advanced on the device
+            elif cache.kmask is not None:
                 kmask = cache.kmask[:, : past + S].contiguous()
         elif attention_mask is not None:
             kmask = attention_mask.bool().contiguous()
@@ -345,7 +358,7 @@ class CambrianLlamaModel(CambrianMetaModel, CBLlamaModel):
                 lat = self.vision_sampler_layers[sites.index(i)](
                     lat.view(n, 1, H), global_context_feature, *feats, *masks, natural_layout=(B, q_side))
                 hidden = SpanMergeFn.apply(hidden, lat.view(n, H), start, q_side)
-        if cache is not None:
+        if cache is not None and cache.slot is None:
             cache.length = past + S
         hidden = self.norm(hidden, hf_cast=not self.training)
         if output_hidden_states:
@@ -508,6 +521,11 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
         check_stop = bool(args.eos_token_ids or args.stopping_criteria)
         if args.streamer is not None:
             args.streamer.put(torch.empty((B, 0), dtype=torch.long))     # HF streams the (here: empty) prompt ids first
+        if (_DECODE_GRAPH and not args.do_sample and z3 is None and max_new > 2 and h_last.is_cuda
+                and not getattr(self.config, "disable_decode_graph", False)):
+            toks = self._generate_graphed(args, cache, h_last, next_pos, S0, max_new, check_stop)
+            self.train(was_training)
+            return toks
         tokens = []
         for step in range(max_new):
             logits = ops.gemm(h_last, self.lm_head.weight, out_dtype=torch.float32)             # fp32 logits (:409)
@@ -529,6 +547,71 @@ class CambrianLlamaForCausalLM(CambrianPreTrainedModel, CambrianMetaForCausalLM)
         if args.streamer is not None:
             args.streamer.end()
         self.train(was_training)
+        return torch.stack(tokens, 1)
+
+    def _generate_graphed(self, args, cache, h_last, next_pos, S0, max_new, check_stop):
+        """Greedy decoding with ONE CUDA graph per generate() call: a decode step is ~290 kernel launches whose device time
+        (weight streaming, a few ms) is far below the cost of enqueueing them one by one from Python (8.3 ms / token for the
+        8B shape, profiles/r02_decode_b1_eager_loop.json), so the step is captured once — static shapes: token / position /
+        cache-slot / validity mask live in device buffers that the captured kernels advance themselves — and replayed per
+        token.  EOS / stopping criteria are evaluated between replays on the host exactly as in the eager loop."""
+        from ...generation import should_stop
+        B = h_last.shape[0]
+        dev = h_last.device
+        pad = args.pad_token_id
+        h_buf = h_last.clone()
+        pos_buf = next_pos.view(B, 1).clone().long()
+        done_buf = torch.zeros(B, dtype=torch.bool, device=dev)
+        tok_buf = torch.zeros(B, dtype=torch.long, device=dev)
+        logits_buf = torch.empty((B, self.lm_head.weight.shape[0]), dtype=torch.float32, device=dev)
+        cache.slot = torch.full((1,), cache.length, dtype=torch.long, device=dev)
+
+        def step():
+            ops.gemm(h_buf, self.lm_head.weight, out=logits_buf)                                 # fp32 logits (:409)
+            nxt = logits_buf.argmax(-1)
+            tok_buf.copy_(torch.where(done_buf, torch.full_like(nxt, pad), nxt))
+            cache.kmask.index_fill_(1, cache.slot, True)
+            out = self.model(input_ids=tok_buf.view(B, 1), position_ids=pos_buf, past_key_values=cache, use_cache=True)
+            h_buf.copy_(out.last_hidden_state[:, 0])
+            pos_buf.add_(1)
+            cache.slot.add_(1)
+
+        # slots beyond the prompt start invalid; each step validates the one it writes
+        cache.kmask[:, S0:] = False
+        snap = (h_buf.clone(), pos_buf.clone(), cache.slot.clone(), cache.kmask.clone())
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up outside capture (lazy kernel attributes, allocator)
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        for buf, s0 in zip((h_buf, pos_buf, cache.slot, cache.kmask), snap):
+            buf.copy_(s0)                                  # the warm-up step advanced the state: rewind (K/V slot S0 is
+        graph = torch.cuda.CUDAGraph()                     # simply rewritten with the same values)
+        with torch.cuda.graph(graph):
+            step()
+        for buf, s0 in zip((h_buf, pos_buf, cache.slot, cache.kmask), snap):
+            buf.copy_(s0)
+        tokens = []
+        for i in range(max_new):
+            if i + 1 == max_new:
+                # the last token needs no further decoder pass: logits -> argmax only
+                logits = ops.gemm(h_buf, self.lm_head.weight, out_dtype=torch.float32)
+                nxt = logits.argmax(-1)
+                tok = torch.where(done_buf, torch.full_like(nxt, pad), nxt)
+            else:
+                graph.replay()
+                tok, logits = tok_buf.clone(), logits_buf
+            tokens.append(tok)
+            if args.streamer is not None:
+                args.streamer.put(tok.cpu())
+            if check_stop:
+                done_buf.copy_(should_stop(args, torch.stack(tokens, 1), logits, done_buf))
+                if bool(done_buf.all()):
+                    break
+        cache.length = S0 + len(tokens)
+        cache.slot = None
+        if args.streamer is not None:
+            args.streamer.end()
         return torch.stack(tokens, 1)
 
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, inputs_embeds=None, **kwargs):

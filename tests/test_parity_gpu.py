@@ -398,6 +398,11 @@ def test_greedy_generate_token_exact_32_tokens():
     imgs = [i[:1].to(dev).bfloat16() for i in images]
     new = model.generate(gen_ids.to(dev), images=imgs, image_sizes=[(56, 56)], max_new_tokens=n_new, do_sample=False)
     got = new[0].tolist()
+    # the same decode as an eager per-token loop (no CUDA graph): identical kernels, identical tokens
+    model.config.disable_decode_graph = True
+    eager_loop = model.generate(gen_ids.to(dev), images=imgs, image_sizes=[(56, 56)], max_new_tokens=n_new, do_sample=False)
+    model.config.disable_decode_graph = False
+    assert torch.equal(new, eager_loop), (new.tolist(), eager_loop.tolist())
     sd = sd_cpu32(model)
     ocfg = oracle_cfg(cfg)
     towers = model.get_model().vision_tower_aux_list

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--prompt", type=int, default=1024)
     ap.add_argument("--new", type=int, default=64)
     ap.add_argument("--config", default="8b-ddp")
+    ap.add_argument("--no-graph", action="store_true", help="eager per-token loop instead of the CUDA-graph replay")
     args = ap.parse_args()
     from cambrian_b200 import _lib
     from cambrian_b200.model.language_model.cambrian_llama import CambrianLlamaForCausalLM
@@ -28,6 +29,7 @@ def main():
     torch.cuda.set_device(0)
     cfg = bench.build_config(args.config)
     cfg.inputs_pre_expanded = False
+    cfg.disable_decode_graph = args.no_graph
     torch.manual_seed(0)
     prev = torch.get_default_dtype()
     torch.set_default_dtype(torch.bfloat16)
@@ -65,7 +67,7 @@ def main():
     floor = n_params * 2 / (hbm * 1e9) * 1e3
     print(json.dumps(dict(metric="decode_ms_per_token", value=ms_tok, unit="ms", batch=B, prompt=args.prompt, new_tokens=args.new,
                           prefill_ms=t1, tokens_per_s=B * 1000.0 / ms_tok, launches_per_token=(ln - l1) / args.new,
-                          weight_bytes=n_params * 2, floor_ms=floor, frac_of_floor=floor / ms_tok,
+                          decode_graph=not args.no_graph, weight_bytes=n_params * 2, floor_ms=floor, frac_of_floor=floor / ms_tok,
                           note="floor = decoder + lm_head bf16 weights / measured HBM copy bandwidth")))
 
 
