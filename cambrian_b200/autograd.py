@@ -571,7 +571,11 @@ class EmbedSpliceFn(torch.autograd.Function):
             else:
                 tgt = torch.zeros(ctx.vshape, dtype=torch.bfloat16, device=dout.device)
                 d_embed_ret = tgt
-        d_img, d_nl_rows = ops.embed_splice_bwd(dout, meta["ids"], meta["img_start"], tgt, meta["q_side"], ctx.has_img)
+        # image / newline rows are plain gathers; the embedding rows are summed per token id in position order
+        # (deterministic: no atomics whose bf16 rounding depends on arrival order)
+        d_img, d_nl_rows = ops.embed_splice_bwd(dout, meta["ids"], meta["img_start"], None, meta["q_side"], ctx.has_img)
+        if tgt is not None:
+            ops.embed_grad_sorted(dout, meta["ids"], meta["img_start"] if ctx.has_img else None, tgt, meta["q_side"])
         if tgt is not None and d_embed_ret is None:
             _notify(p_embed)
         d_nl = None

@@ -69,6 +69,7 @@ int embed_splice_launch(const long long*, const int*, const void*, const void*, 
                         long long, cudaStream_t);
 int embed_splice_bwd_launch(const void*, const long long*, const int*, void*, void*, void*, int, int, int, int,
                             long long, cudaStream_t);
+int embed_grad_sorted_launch(const void*, const long long*, const int*, void*, long long, int, long long, cudaStream_t);
 int add_pos_tokens_launch(const void*, const void*, const void*, void*, int, int, int, cudaStream_t);
 int bilinear_launch(const void*, void*, int, int, int, int, int, int, long long, long long, int, int, cudaStream_t);
 int patchify_nchw_launch(const void*, void*, int, int, int, int, int, cudaStream_t);
@@ -294,6 +295,11 @@ int cb_adamw_ex(float* p, float* m, float* v, const void* g, void* p16, int64_t 
                 void* stream) {
   return cb::adamw_launch(p, m, v, g, p16, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, clip_coef, background,
                           ST(stream));
+}
+int cb_embed_grad_sorted(const void* dout, const int64_t* keys, const int32_t* order, void* d_embed, int64_t n, int H,
+                         int64_t vocab, void* stream) {
+  return cb::embed_grad_sorted_launch(dout, reinterpret_cast<const long long*>(keys), order, d_embed, n, H, vocab,
+                                      ST(stream));
 }
 int cb_gemm_set_dynamic_scheduling(int on) { return cb::gemm_set_dynamic_scheduling(on); }
 int cb_sumsq_bf16(const void* g, int64_t n, float* acc, float* workspace, int64_t workspace_floats, int background,

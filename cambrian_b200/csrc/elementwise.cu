@@ -218,6 +218,38 @@ __global__ void embed_splice_bwd_kernel(const bf16* __restrict__ dout, const lon
   }
 }
 
+// Deterministic embedding-row gradient: the rows of `dout` that belong to the same token id are summed by ONE block in
+// position order (fp32) and written once, instead of racing bf16x2 atomics whose rounding depends on arrival order.
+// keys[t] = token id of flattened position t, or >= vocab for positions that carry no embedding gradient (image span);
+// order = positions stably sorted by key.  d_embed += (single writer per row: still deterministic); ids that do not occur
+// are not touched.
+__global__ void __launch_bounds__(128)
+embed_grad_sorted_kernel(const bf16* __restrict__ dout, const long long* __restrict__ keys, const int* __restrict__ order,
+                         bf16* __restrict__ d_embed, long long n, int H, long long vocab) {
+  const long long p = blockIdx.x;
+  const long long key = keys[order[p]];
+  if (key < 0 || key >= vocab) return;
+  if (p > 0 && keys[order[p - 1]] == key) return;  // not the first position of this id's segment
+  const int vpr = H >> 3;
+  for (int v = threadIdx.x; v < vpr; v += blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long q = p; q < n; ++q) {
+      const long long t = order[q];
+      if (keys[t] != key) break;
+      float f[8];
+      unpack8(ldg_nc(reinterpret_cast<const uint4*>(dout + t * H) + v), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+    uint4* dst = reinterpret_cast<uint4*>(d_embed + key * H) + v;
+    float old[8];
+    unpack8(*dst, old);  // += : zero on the first micro-batch of a step, the running sum under gradient accumulation
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += old[e];
+    *dst = pack8(acc);
+  }
+}
+
 // --------------------------------------------------------------------------- ViT token assembly
 // out[b, 0] = cls + pos[0] (if cls);  out[b, c + i] = patch[b, i] + pos[c + i]
 // (HF CLIPVisionEmbeddings / Dinov2Embeddings / timm _pos_embed, reached from clip_encoder.py:104 etc.)
@@ -832,6 +864,14 @@ int embed_splice_bwd_launch(const void* dout, const long long* ids, const int* i
   embed_splice_bwd_kernel<<<grid_for((long long)B * S * (H / 8), 256), 256, 0, st>>>(
       (const bf16*)dout, ids, img_start, (bf16*)d_embed, (bf16*)d_img, (bf16*)d_nl_rows, B, S, H, q_side, vocab);
   CB_CUDA_LAUNCH_CHECK("embed_splice_bwd");
+  return CB_OK;
+}
+int embed_grad_sorted_launch(const void* dout, const long long* keys, const int* order, void* d_embed, long long n, int H,
+                             long long vocab, cudaStream_t st) {
+  VEC_CHECK(H, "embed_grad_sorted");
+  CB_CHECK_ARG(dout && keys && order && d_embed && n > 0 && vocab > 0, "embed_grad_sorted: bad arguments");
+  embed_grad_sorted_kernel<<<(unsigned)n, 128, 0, st>>>((const bf16*)dout, keys, order, (bf16*)d_embed, n, H, vocab);
+  CB_CUDA_LAUNCH_CHECK("embed_grad_sorted");
   return CB_OK;
 }
 int add_pos_tokens_launch(const void* patch, const void* cls, const void* pos, void* out, int B, int N, int C,

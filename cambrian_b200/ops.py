@@ -381,6 +381,24 @@ def embed_splice_bwd(dout, ids, img_start, d_embed, q_side: int, has_img: bool):
     return d_img, d_nl
 
 
+def embed_grad_sorted(dout, ids, img_start, d_embed, q_side: int):
+    """Deterministic embedding-row gradient: d_embed[id] = sum over the text positions holding `id` of dout rows, summed in
+    position order (d_embed must be zero on entry).  The sort of 8 K token ids is device-side index plumbing (torch)."""
+    B, S, H = dout.shape
+    vocab = d_embed.shape[0]
+    keys = ids.reshape(B, S).clamp(min=0)
+    keys = torch.where(keys >= vocab, torch.zeros_like(keys), keys)
+    if img_start is not None:
+        span = q_side * (q_side + 1)
+        pos = torch.arange(S, device=ids.device)[None]
+        st = img_start.to(torch.long)[:, None]
+        keys = torch.where((st >= 0) & (pos >= st) & (pos < st + span), torch.full_like(keys, vocab), keys)
+    keys = keys.reshape(-1).contiguous()
+    order = torch.argsort(keys, stable=True).to(torch.int32)
+    check(_lib.load().cb_embed_grad_sorted(ptr(dout), ptr(keys), ptr(order), ptr(d_embed), B * S, H, vocab, stream()),
+          "cb_embed_grad_sorted")
+
+
 def add_pos_tokens(patch, cls, pos):
     B, N, C_ = patch.shape
     T = N + (1 if cls is not None else 0)

@@ -211,6 +211,12 @@ int cb_adamw(float* p, float* m, float* v, const void* g, void* p16, int64_t n, 
 int cb_adamw_ex(float* p, float* m, float* v, const void* g, void* p16, int64_t n, float lr, float beta1, float beta2,
                 float eps, float weight_decay, int step, float grad_scale, const float* clip_coef, int background,
                 void* stream);
+/* Deterministic gradient of the embedding rows (backward of embed_tokens inside cb_embed_splice): rows of dout [n, H] with
+ * equal keys[t] (token id; >= vocab = no gradient, e.g. the image span) are summed in position order by one block and
+ * written once to d_embed [vocab, H] (pre-zeroed).  `order` = positions stably sorted by key.  Replaces the racing
+ * bf16x2 atomics of cb_embed_splice_bwd (pass d_embed = NULL there). */
+int cb_embed_grad_sorted(const void* dout, const int64_t* keys, const int32_t* order, void* d_embed, int64_t n, int H,
+                         int64_t vocab, void* stream);
 /* GEMM tile scheduling: 1 (default; env CB_GEMM_CLC=0 to start with 0) = one CTA / CTA pair per tile in the grid, tiles
  * handed out by Cluster Launch Control so the GEMM tolerates SMs held by collectives / the background optimizer;
  * 0 = static persistent walk.  Returns the previous setting.  Results are bit-identical either way. */

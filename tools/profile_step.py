@@ -1,5 +1,7 @@
 """Runs the bench workload for a few warm-up steps, then brackets ONE training step with cudaProfilerStart/Stop so that
-`ncu --profile-from-start off ...` captures exactly that step (see profiles/README.md for the commands)."""
+`ncu --profile-from-start off ...` captures exactly that step (see profiles/README.md for the commands).  With CB_NVTX=1
+every block of the step carries an NVTX range (decoder_layer.fwd / .bwd, sva_layer.*, tower.*, lm_head_loss.*,
+optimizer.bucketN)."""
 import argparse
 import os
 import sys
@@ -12,17 +14,18 @@ import bench  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--micro-batch", type=int, default=4)
+    ap.add_argument("--config", default="8b-ddp")
+    ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--recompute", type=int, default=0)
     a = ap.parse_args()
-    args = argparse.Namespace(small=a.small)
     from cambrian_b200.engine import TrainEngine
     from cambrian_b200.model.language_model.cambrian_llama import CambrianLlamaForCausalLM
     dev = torch.device("cuda", 0)
-    cfg = bench.cambrian_8b_config(args)
-    res = bench.TOWER_RES if not a.small else [384, 336, 336, 256]
+    C = bench.CONFIGS[a.config]
+    cfg = bench.build_config(a.config, a.small)
+    res = C["res"] if not a.small else [r if r < 1024 else 256 for r in C["res"]]
     torch.manual_seed(1234)
     torch.set_default_dtype(torch.bfloat16)
     with torch.device(dev):
@@ -32,22 +35,25 @@ def main():
     torch.set_default_dtype(torch.float32)
     model.train()
     model.get_model().gradient_checkpointing = bool(a.recompute)
-    eng = TrainEngine(model)
-    hb, (nv, lr) = bench.make_host_batch(cfg, a.micro_batch, 2048, 0, res)
-    db, _ = bench.to_device(hb, dev)
-    pos = [cfg.image_position] * a.micro_batch
+    eng = TrainEngine(model, max_grad_norm=1.0)
+    eng.defer_param_sync = True
+    B = a.micro_batch or C["micro_batch"]
+    S = C["seq"] if not a.small else 1024
+    db, _ = bench.to_device(bench.make_host_batch(cfg, B, S, 0, res, True), dev)
 
     def step():
         eng.zero_grad()
-        out = model(**db, num_valid_labels=nv, image_positions=pos, label_ranges=lr)
+        out = model(**db)
         out.loss.backward()
         eng.step()
 
     for _ in range(a.warmup):
         step()
+    eng.wait_for_params()
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     step()
+    eng.wait_for_params()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 
