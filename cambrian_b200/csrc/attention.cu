@@ -529,8 +529,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_ss(tB, make_smem_desc_sw128(sdS + kk * 2048, 16384, 1024),
                   make_smem_desc_sw128(sK + kk * 2048, 16384, 1024), idesc_dq, kk ? 1u : 0u);
         }
-        umma_commit(qd_empty(st));
-        umma_commit(dq_full);
+        umma_commit(dq_full);  // (the Q / dO stage is handed back through dq_staged: see the producer)
         if (++st == 2) { st = 0; ph ^= 1u; }
       }
     }

@@ -665,6 +665,8 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 1) tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   cluster_sync_all();  // barrier inits + TMEM allocation of both CTAs visible before any cross-CTA traffic
+  __syncthreads();     // (the cluster barrier already orders this; a CTA barrier is what compute-sanitizer racecheck models
+                       //  between tcgen05.alloc's shared-memory write and the read below — one-time cost)
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));

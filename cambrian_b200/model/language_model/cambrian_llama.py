@@ -216,8 +216,10 @@ class KVCache:
         nkv = config.num_key_value_heads
         hd = getattr(config, "head_dim", None) or config.hidden_size // config.num_attention_heads
         L = config.num_hidden_layers
-        self.k = [torch.empty((batch, max_len, nkv, hd), dtype=torch.bfloat16, device=device) for _ in range(L)]
-        self.v = [torch.empty((batch, max_len, nkv, hd), dtype=torch.bfloat16, device=device) for _ in range(L)]
+        # zero-initialised: the static-shape decode step attends over the WHOLE buffer with not-yet-written slots masked
+        # out — their probabilities are exactly 0, but 0 x (uninitialised NaN / Inf bit patterns in V) would still be NaN
+        self.k = [torch.zeros((batch, max_len, nkv, hd), dtype=torch.bfloat16, device=device) for _ in range(L)]
+        self.v = [torch.zeros((batch, max_len, nkv, hd), dtype=torch.bfloat16, device=device) for _ in range(L)]
         self.length = 0
         self.max_len = max_len
         self.kmask = None  # [B, max_len] bool, key validity over the whole cache

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--new", type=int, default=64)
     ap.add_argument("--config", default="8b-ddp")
     ap.add_argument("--no-graph", action="store_true", help="eager per-token loop instead of the CUDA-graph replay")
+    ap.add_argument("--profile", action="store_true", help="kernel time per token by kernel name (torch.profiler)")
     args = ap.parse_args()
     from cambrian_b200 import _lib
     from cambrian_b200.model.language_model.cambrian_llama import CambrianLlamaForCausalLM
@@ -65,10 +66,23 @@ def main():
                    and "embed_tokens" not in n)
     hbm = bench.peaks()[0]
     floor = n_params * 2 / (hbm * 1e9) * 1e3
+    top = None
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run(args.new + 1)
+        agg = {}
+        for e in prof.events():
+            if e.device_type is not None and "cuda" in str(e.device_type).lower() and e.device_time > 0:
+                a_ = agg.setdefault(e.name[:70], [0.0, 0])
+                a_[0] += e.device_time
+                a_[1] += 1
+        top = [dict(kernel=k, ms_per_token=round(v[0] / 1e3 / args.new, 4), launches_per_token=round(v[1] / args.new, 1))
+               for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]]
     print(json.dumps(dict(metric="decode_ms_per_token", value=ms_tok, unit="ms", batch=B, prompt=args.prompt, new_tokens=args.new,
                           prefill_ms=t1, tokens_per_s=B * 1000.0 / ms_tok, launches_per_token=(ln - l1) / args.new,
                           decode_graph=not args.no_graph, weight_bytes=n_params * 2, floor_ms=floor, frac_of_floor=floor / ms_tok,
-                          note="floor = decoder + lm_head bf16 weights / measured HBM copy bandwidth")))
+                          note="floor = decoder + lm_head bf16 weights / measured HBM copy bandwidth", top_kernels=top)))
 
 
 if __name__ == "__main__":

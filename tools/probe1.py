@@ -212,6 +212,21 @@ def group_gemm_clc():
     ops.gemm_set_dynamic_scheduling(True)
 
 
+def group_gemv():
+    """Decode-shaped (M <= 8) projections: achieved weight-streaming bandwidth of the tcgen05 GEMM per shape."""
+    for (N, K) in ((6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336), (128256, 4096)):
+        w = torch.randn(N, K, device=dev).bfloat16() * 0.02
+        for M in (1, 8):
+            x = torch.randn(M, K, device=dev).bfloat16()
+            for bn in (0, 64, 128, 256):
+                try:
+                    ms = timeit(lambda: ops.gemm(x, w, force_bn=bn), iters=30)
+                except Exception as ex:
+                    print(f"gemv M={M} N={N} K={K} bn={bn}: {ex}")
+                    continue
+                print(f"gemv M={M} N={N} K={K} bn={bn}: {ms * 1e3:8.1f} us  {N * K * 2 / ms / 1e6:7.0f} GB/s", flush=True)
+
+
 def group_gemm_perf():
     for (M, N, K) in [(8192, 8192, 8192), (8192, 14336, 4096), (8192, 4096, 14336), (4096, 4096, 4096),
                       (2304, 1024, 1024)]:
