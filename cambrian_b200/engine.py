@@ -282,9 +282,9 @@ class TrainEngine:
             self._sumsq_ws = torch.empty(4096, dtype=torch.float32, device=g.device)
         if st is not None:
             with torch.cuda.stream(st):
-                ops.sumsq_accumulate(g, self._sumsq, self._sumsq_ws)
+                ops.sumsq_accumulate(g, self._sumsq, self._sumsq_ws, background=self.background)
         else:
-            ops.sumsq_accumulate(g, self._sumsq, self._sumsq_ws)
+            ops.sumsq_accumulate(g, self._sumsq, self._sumsq_ws, background=self.background)
 
     def _update_bucket(self, b, side: bool):
         """Fused AdamW over bucket b's segments (this rank's piece under ZeRO-2), then the in-place all-gather of the updated
