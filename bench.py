@@ -437,6 +437,7 @@ def main():
     engine = TrainEngine(model, lr=4e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, zero_stage=C["zero"],
                          max_grad_norm=args.max_grad_norm, bucket_mb=args.bucket_mb,
                          overlap=os.environ.get("CB_OVERLAP", "1") != "0",
+                         collective=os.environ.get("CB_COLLECTIVE", "nccl"),
                          background_optimizer=os.environ.get("CB_BACKGROUND_OPT", "0") != "0")
     engine.defer_param_sync = os.environ.get("CB_DEFER_PARAM_SYNC", "1") != "0"   # consumers wait per bucket
     n_train = sum(p.numel() for p in engine.params)

@@ -86,6 +86,8 @@ int adamw_launch(float*, float*, float*, const void*, void*, long long, float, f
                  const float*, int, cudaStream_t);
 int sumsq_launch(const void*, long long, float*, float*, long long, int, cudaStream_t);
 int gemm_set_dynamic_scheduling(int);
+int allreduce_symm_launch(unsigned long long, const unsigned long long*, const unsigned long long*, long long, long long, int,
+                          int, unsigned int, int, cudaStream_t);
 int clip_coef_launch(float*, float, float, float*, cudaStream_t);
 int span_gather_launch(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int span_scatter_launch(void*, const void*, int, int, int, int, int, int, cudaStream_t);
@@ -300,6 +302,12 @@ int cb_embed_grad_sorted(const void* dout, const int64_t* keys, const int32_t* o
                          int64_t vocab, void* stream) {
   return cb::embed_grad_sorted_launch(dout, reinterpret_cast<const long long*>(keys), order, d_embed, n, H, vocab,
                                       ST(stream));
+}
+int cb_allreduce_symm_bf16(uint64_t multicast_base, const uint64_t* buffer_ptrs, const uint64_t* signal_pad_ptrs,
+                           int64_t offset_bytes, int64_t nbytes, int rank, int world, uint32_t epoch, int ctas, void* stream) {
+  return cb::allreduce_symm_launch(multicast_base, reinterpret_cast<const unsigned long long*>(buffer_ptrs),
+                                   reinterpret_cast<const unsigned long long*>(signal_pad_ptrs), offset_bytes, nbytes, rank,
+                                   world, epoch, ctas, ST(stream));
 }
 int cb_gemm_set_dynamic_scheduling(int on) { return cb::gemm_set_dynamic_scheduling(on); }
 int cb_sumsq_bf16(const void* g, int64_t n, float* acc, float* workspace, int64_t workspace_floats, int background,

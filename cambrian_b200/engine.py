@@ -46,6 +46,16 @@ def _round_up(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
+class _EventHandle:
+    """`Work.wait()` look-alike for our own collective kernel: makes the CURRENT stream wait for the recorded event."""
+
+    def __init__(self, ev):
+        self.ev = ev
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.ev)
+
+
 def cosine_schedule_with_warmup(num_warmup_steps: int, num_training_steps: int, num_cycles: float = 0.5):
     """`lr_lambda` equal to transformers.get_cosine_schedule_with_warmup (the reference scripts train with
     `--lr_scheduler_type cosine --warmup_ratio 0.03`, scripts/cambrian/finetune_cambrian_8b.sh): step -> multiplier."""
@@ -64,7 +74,7 @@ class TrainEngine:
                  weight_decay: float = 0.0, bucket_mb: float = 256.0, process_group=None, overlap: bool = True,
                  zero_stage: int = 0, max_grad_norm: float | None = None, mm_projector_lr: float | None = None,
                  mm_vision_sampler_lr: float | None = None, lr_lambda=None, loss_scale: float = 1.0,
-                 background_optimizer: bool = False):
+                 background_optimizer: bool = False, collective: str = "nccl"):
         if zero_stage not in (0, 2):
             raise ValueError("zero_stage must be 0 or 2")
         if mm_projector_lr is not None and mm_vision_sampler_lr is not None:
@@ -75,6 +85,8 @@ class TrainEngine:
         self.lr_lambda = lr_lambda            # step (0-based, as torch LambdaLR) -> multiplier of every group's lr
         self.loss_scale = float(loss_scale)   # e.g. 1 / gradient_accumulation_steps; folded into the fused loss gradient
         self.background = background_optimizer
+        if collective not in ("nccl", "multimem", "p2p"):
+            raise ValueError("collective must be 'nccl', 'multimem' (in-switch NVLS all-reduce kernel) or 'p2p'")
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
@@ -106,7 +118,8 @@ class TrainEngine:
             self.hparams.append((glr, decay))
         # ---- flat layout + buckets: contiguous parameter ranges of ~bucket_mb; with ZeRO-2 every bucket is padded to a
         #      multiple of 8 * world elements so each rank owns an equal, 16-byte aligned piece of it
-        align = 8 * self.world if zero_stage == 2 else 8
+        self.collective = collective if (self.world > 1 and zero_stage == 0) else "nccl"
+        align = 8 * self.world if (zero_stage == 2 or self.collective != "nccl") else 8
         limit = int(bucket_mb * 1024 * 1024 / 2)
         offs, total = [], 0
         self.buckets = []      # (start_elem, end_elem, [param indices])
@@ -125,7 +138,17 @@ class TrainEngine:
         self.offsets = offs
         self.total = total
         self.flat_p = torch.zeros(total, dtype=torch.bfloat16, device=dev)
-        self.flat_g = torch.zeros(total, dtype=torch.bfloat16, device=dev)
+        self._symm = self._comm_stream = None
+        if self.collective != "nccl":
+            # gradients live in a symmetric allocation every rank maps (and the switch multicasts into): comm.py
+            from .comm import SymmetricAllReduce
+            import os
+            self._symm = SymmetricAllReduce(total, dev, process_group, ctas=int(os.environ.get("CB_AR_CTAS", "16")),
+                                            use_multicast=self.collective == "multimem")
+            self.flat_g = self._symm.buf
+            self._comm_stream = torch.cuda.Stream(device=dev)
+        else:
+            self.flat_g = torch.zeros(total, dtype=torch.bfloat16, device=dev)
         self._bucket_of = {}
         for b, (_, _, idx) in enumerate(self.buckets):
             for i in idx:
@@ -237,6 +260,15 @@ class TrainEngine:
         s, e, _ = self.buckets[b]
         self._launched[b] = True
         if self.world == 1:
+            return
+        if self._symm is not None:
+            cs = self._comm_stream
+            cs.wait_stream(torch.cuda.current_stream())        # after the bucket's last gradient write
+            with torch.cuda.stream(cs):
+                self._symm.all_reduce_(s, e)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            self._handles[b] = _EventHandle(ev)
             return
         if self.zero_stage == 2:
             lo, hi = self._piece(b)

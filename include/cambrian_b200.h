@@ -217,6 +217,14 @@ int cb_adamw_ex(float* p, float* m, float* v, const void* g, void* p16, int64_t 
  * bf16x2 atomics of cb_embed_splice_bwd (pass d_embed = NULL there). */
 int cb_embed_grad_sorted(const void* dout, const int64_t* keys, const int32_t* order, void* d_embed, int64_t n, int H,
                          int64_t vocab, void* stream);
+/* In-place sum all-reduce of the bf16 range [offset_bytes, +nbytes) of a SYMMETRIC buffer (same offset on every rank) —
+ * the bucketed gradient reduction of the data-parallel step (reference: inside torch_xla FSDP; explicit helper
+ * cambrian_trainer.py:181-190).  multicast_base != 0: NVLS path (multimem.ld_reduce / multimem.st, the NVSwitch adds and
+ * fans out); 0: peer loads / stores over NVLink.  buffer_ptrs / signal_pad_ptrs: HOST arrays of `world` peer-mapped device
+ * addresses (this rank's own included).  epoch: strictly increasing across launches on all ranks alike, advance by 2 per
+ * call.  nbytes % (16 * world) == 0.  Every rank must issue the same calls in the same order. */
+int cb_allreduce_symm_bf16(uint64_t multicast_base, const uint64_t* buffer_ptrs, const uint64_t* signal_pad_ptrs,
+                           int64_t offset_bytes, int64_t nbytes, int rank, int world, uint32_t epoch, int ctas, void* stream);
 /* GEMM tile scheduling: 1 (default; env CB_GEMM_CLC=0 to start with 0) = one CTA / CTA pair per tile in the grid, tiles
  * handed out by Cluster Launch Control so the GEMM tolerates SMs held by collectives / the background optimizer;
  * 0 = static persistent walk.  Returns the previous setting.  Results are bit-identical either way. */
