@@ -86,6 +86,8 @@ int adamw_launch(float*, float*, float*, const void*, void*, long long, float, f
                  const float*, int, cudaStream_t);
 int sumsq_launch(const void*, long long, float*, float*, long long, int, cudaStream_t);
 int gemm_set_dynamic_scheduling(int);
+int gemv_bf16_launch(const void*, const void*, void*, int, int, int, long long, long long, long long, const void*, const void*,
+                     long long, int, cudaStream_t);
 int allreduce_symm_launch(unsigned long long, const unsigned long long*, const unsigned long long*, long long, long long, int,
                           int, unsigned int, int, cudaStream_t);
 int clip_coef_launch(float*, float, float, float*, cudaStream_t);
@@ -308,6 +310,10 @@ int cb_allreduce_symm_bf16(uint64_t multicast_base, const uint64_t* buffer_ptrs,
   return cb::allreduce_symm_launch(multicast_base, reinterpret_cast<const unsigned long long*>(buffer_ptrs),
                                    reinterpret_cast<const unsigned long long*>(signal_pad_ptrs), offset_bytes, nbytes, rank,
                                    world, epoch, ctas, ST(stream));
+}
+int cb_gemv_bf16(const void* x, const void* w, void* y, int M, int N, int K, int64_t ldx, int64_t ldw, int64_t ldy,
+                 const void* bias, const void* residual, int64_t ldr, int out_fp32, void* stream) {
+  return cb::gemv_bf16_launch(x, w, y, M, N, K, ldx, ldw, ldy, bias, residual, ldr, out_fp32, ST(stream));
 }
 int cb_gemm_set_dynamic_scheduling(int on) { return cb::gemm_set_dynamic_scheduling(on); }
 int cb_sumsq_bf16(const void* g, int64_t n, float* acc, float* workspace, int64_t workspace_floats, int background,

@@ -102,6 +102,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     N, Kb = (bc, br) if b_mn else (br, bc)
     if K != Kb or ba != bb:
         raise ValueError(f"gemm: shape mismatch a={tuple(a.shape)} b={tuple(b.shape)} a_mn={a_mn} b_mn={b_mn}")
+    if (_GEMV and M <= 8 and not batched and not a_mn and not b_mn and act in (None, "none") and colscale is None
+            and not accumulate and alpha == 1.0 and force_bn == 0 and K % 8 == 0 and lda % 8 == 0 and ldb % 8 == 0
+            and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
+        return gemv(a, b, bias=bias, residual=residual, out=out, out_dtype=out_dtype)      # decode step: weight streaming
     if out is None:
         if accumulate:
             raise ValueError("gemm: accumulate=True needs an explicit `out`")
@@ -122,6 +126,26 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                                   float(alpha), ACT[act], int(out.dtype == torch.float32), int(accumulate),
                                   int(force_bn), stream())
     check(rc, "cb_gemm_bf16")
+    return out
+
+
+_GEMV = os.environ.get("CB_GEMV", "1") != "0"
+
+
+def gemv(x: torch.Tensor, w: torch.Tensor, bias=None, residual=None, out=None, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """y[M, N] = x[M, K] @ w[N, K]^T (+ bias) (+ residual) for M <= 8 (the KV-cache decode step)."""
+    _require_cuda_bf16(x, w, bias, residual)
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    if out.dtype not in (torch.bfloat16, torch.float32) or out.stride(-1) != 1 or out.shape != (M, N):
+        raise ValueError("gemv: out must be a bf16 / fp32 [M, N] tensor with contiguous rows")
+    if residual is not None and (residual.shape != out.shape or residual.stride(-1) != 1):
+        raise ValueError("gemv: residual must match the output shape")
+    check(_lib.load().cb_gemv_bf16(ptr(x), ptr(w), ptr(out), M, N, K, x.stride(0), w.stride(0), out.stride(0), ptr(bias),
+                                   ptr(residual), residual.stride(0) if residual is not None else 0,
+                                   int(out.dtype == torch.float32), stream()), "cb_gemv_bf16")
     return out
 
 

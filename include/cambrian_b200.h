@@ -217,6 +217,11 @@ int cb_adamw_ex(float* p, float* m, float* v, const void* g, void* p16, int64_t 
  * bf16x2 atomics of cb_embed_splice_bwd (pass d_embed = NULL there). */
 int cb_embed_grad_sorted(const void* dout, const int64_t* keys, const int32_t* order, void* d_embed, int64_t n, int H,
                          int64_t vocab, void* stream);
+/* Decode-shaped projection, M <= 8 rows: y[M,N] = x[M,K] W[N,K]^T (+ bias[N]) (+ residual[M,N]); W in nn.Linear layout.
+ * Weight-streaming CUDA-core kernel (each weight byte read once, fp32 accumulation) used by the KV-cache decode step of
+ * generate() (cambrian_llama.py:437-483) where a 128-row tensor-core tile would idle; y bf16 or fp32 (lm_head logits). */
+int cb_gemv_bf16(const void* x, const void* w, void* y, int M, int N, int K, int64_t ldx, int64_t ldw, int64_t ldy,
+                 const void* bias, const void* residual, int64_t ldr, int out_fp32, void* stream);
 /* In-place sum all-reduce of the bf16 range [offset_bytes, +nbytes) of a SYMMETRIC buffer (same offset on every rank) —
  * the bucketed gradient reduction of the data-parallel step (reference: inside torch_xla FSDP; explicit helper
  * cambrian_trainer.py:181-190).  multicast_base != 0: NVLS path (multimem.ld_reduce / multimem.st, the NVSwitch adds and

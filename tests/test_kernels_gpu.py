@@ -37,6 +37,10 @@ def test_gemm_dynamic_scheduling_is_bit_identical(capsys):
     _run("probe1", "gemm_clc", capsys, 12)
 
 
+def test_decode_gemv(capsys):
+    _run("probe1", "gemv", capsys, 6)
+
+
 def test_gemm_cta_pair_kernel(capsys):
     _run("probe1", "gemm_2cta", capsys, 24)
 

@@ -213,18 +213,34 @@ def group_gemm_clc():
 
 
 def group_gemv():
-    """Decode-shaped (M <= 8) projections: achieved weight-streaming bandwidth of the tcgen05 GEMM per shape."""
+    """Decode-shaped (M <= 8) projections: the weight-streaming GEMV vs an fp32 reference (bias / residual / fp32 output /
+    ragged N and K tails), and the achieved weight bandwidth of GEMV and of the 128-row tcgen05 tile on the same shapes."""
+    for (M, N, K, bias, res, f32) in [(1, 4096, 4096, False, True, False), (3, 520, 1032, True, False, False),
+                                      (8, 6144, 4096, False, False, False), (5, 1000, 2056, True, True, True),
+                                      (8, 128256, 4096, False, False, True), (2, 4096, 14336, False, True, False)]:
+        x = torch.randn(M, K, device=dev).bfloat16()
+        w = torch.randn(N, K, device=dev).bfloat16() * 0.05
+        b = torch.randn(N, device=dev).bfloat16() if bias else None
+        r = torch.randn(M, N, device=dev).bfloat16() if res else None
+        ref = x.float() @ w.float().t()
+        if bias:
+            ref = ref + b.float()
+        if res:
+            ref = ref + r.float()
+        got = ops.gemv(x, w, bias=b, residual=r, out_dtype=torch.float32 if f32 else torch.bfloat16)
+        e = rel_err(got, ref)
+        tol = 2e-5 if f32 else 1e-2
+        print(f"gemv M={M} N={N} K={K} bias={int(bias)} res={int(res)} fp32={int(f32)}: err {e:.2e} {'OK' if e < tol else 'FAIL'}", flush=True)
     for (N, K) in ((6144, 4096), (4096, 4096), (28672, 4096), (4096, 14336), (128256, 4096)):
         w = torch.randn(N, K, device=dev).bfloat16() * 0.02
         for M in (1, 8):
             x = torch.randn(M, K, device=dev).bfloat16()
-            for bn in (0, 64, 128, 256):
-                try:
-                    ms = timeit(lambda: ops.gemm(x, w, force_bn=bn), iters=30)
-                except Exception as ex:
-                    print(f"gemv M={M} N={N} K={K} bn={bn}: {ex}")
-                    continue
-                print(f"gemv M={M} N={N} K={K} bn={bn}: {ms * 1e3:8.1f} us  {N * K * 2 / ms / 1e6:7.0f} GB/s", flush=True)
+            t_v = timeit(lambda: ops.gemv(x, w), iters=30)
+            ops._GEMV = False
+            t_t = timeit(lambda: ops.gemm(x, w), iters=30)
+            ops._GEMV = True
+            print(f"gemv perf M={M} N={N} K={K}: gemv {t_v * 1e3:7.1f} us {N * K * 2 / t_v / 1e6:6.0f} GB/s | tcgen05 tile "
+                  f"{t_t * 1e3:7.1f} us {N * K * 2 / t_t / 1e6:6.0f} GB/s", flush=True)
 
 
 def group_gemm_perf():
