@@ -70,7 +70,7 @@ def main():
     g = torch.Generator().manual_seed(100 + rank)
     ids = torch.randint(3, cfg.vocab_size, (1, a.prompt), generator=g)
     ids[0, cfg.image_position] = -200
-    images = [torch.randn(1, 3, r, r, generator=g).bfloat16().to(dev) for r in bench.TOWER_RES]
+    images = [torch.randn(1, 3, r, r, generator=g).bfloat16().to(dev) for r in bench.CONFIGS["8b-ddp"]["res"]]
     ids = ids.to(dev)
 
     def run(n_new):
