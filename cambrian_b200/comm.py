@@ -15,11 +15,11 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import check
 
-FLAG_WORDS = 32 * 8          # AR_MAX_CTAS x AR_MAX_RANKS (collective.cu)
+FLAG_WORDS = 160 * 8         # AR_MAX_CTAS x AR_MAX_RANKS (collective.cu)
 
 
 class SymmetricAllReduce:
-    def __init__(self, numel: int, device, group=None, ctas: int = 16, use_multicast: bool = True):
+    def __init__(self, numel: int, device, group=None, ctas: int = 0, use_multicast: bool = True):
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -38,7 +38,9 @@ class SymmetricAllReduce:
         self.flag_ptrs = (ctypes.c_uint64 * self.world)(*[int(p) for p in hf.buffer_ptrs])
         mc = int(getattr(hb, "multicast_ptr", 0) or 0)
         self.multicast = mc if use_multicast else 0
-        self.ctas = int(ctas)
+        # 128-thread CTAs that share SMs with the GEMM CTAs: one per SM keeps enough switch round trips in flight at any
+        # world size (each GPU moves 1/world of a bucket through its own loads / stores)
+        self.ctas = int(ctas) if ctas else min(148, _lib.load().cb_sm_count())
         self.epoch = 1
         dist.barrier(group=self.group)                   # every rank's flags are zero before anyone raises one
 

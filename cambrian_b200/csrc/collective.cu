@@ -3,13 +3,13 @@
 // cambrian_trainer.py:181-190).
 //
 // Every rank holds its gradient bucket at the SAME offset of a symmetric allocation that is also mapped through an NVLS
-// multicast address.  One kernel per bucket, a handful of CTAs per GPU:
+// multicast address.  One kernel per bucket, small (128-thread) CTAs that co-reside with the GEMM CTAs of the backward pass:
 //     barrier            every rank has finished writing its copy of the bucket (kernel boundary + release/acquire flags)
 //     reduce + publish   rank r owns slice r of the bucket: `multimem.ld_reduce` asks the SWITCH for the fp32-accumulated sum
 //                        of that 16-byte chunk over all ranks' copies, `multimem.st` multicasts the bf16 result back into
 //                        every rank's copy.  Each GPU therefore issues loads / stores for only 1/world of the bucket — the
-//                        reduction arithmetic and the fan-out happen in the NVSwitch, not in SM instructions — which is why
-//                        4-16 CTAs reach link rate and the persistent GEMMs of the backward pass keep the other SMs.
+//                        reduction arithmetic and the fan-out happen in the NVSwitch, not in SM instructions — so the
+//                        SM-side cost is a few thousand threads of loads in flight, not whole SMs.
 //     barrier            every rank has published its slice: the whole bucket is final everywhere.
 // Without multicast support (no NVSwitch fabric) the same schedule runs on plain peer pointers: the owner of a slice loads it
 // from every peer over NVLink, adds in fp32 and stores the result to every peer.
@@ -23,7 +23,9 @@
 namespace cb {
 
 constexpr int AR_MAX_RANKS = 8;
-constexpr int AR_MAX_CTAS = 32;
+constexpr int AR_MAX_CTAS = 160;
+constexpr int AR_THREADS = 128;  // 4 warps x 32 registers: fits NEXT TO a resident GEMM CTA (320 threads, 54 K registers, no
+                                  // smem of ours) on the same SM — the collective does not take SMs away from the backward pass
 constexpr int AR_PAD_WORDS_OFFSET = 0;     // the flag words live in their own small symmetric allocation (comm.py)
 
 struct ArPeers {
@@ -56,8 +58,36 @@ __device__ __forceinline__ void cross_rank_barrier(const ArPeers& peers, int ran
   __syncthreads();
 }
 
+__device__ __forceinline__ uint4 mm_ld_reduce(unsigned long long addr) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void mm_st(unsigned long long addr, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 p2p_reduce(const ArPeers& peers, int world, long long c) {
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int p = 0; p < world; ++p) {
+    uint4 v;  // peer (or own) copy through the NVLink mapping: bypass L1, the data was just written by another GPU's kernels
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(reinterpret_cast<const uint4*>(peers.buf[p]) + c)
+                 : "memory");
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+  return pack8(acc);
+}
+
 template <bool MULTIMEM>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(AR_THREADS)
 allreduce_bf16_kernel(unsigned long long mc_base, ArPeers peers, long long offset_bytes, long long nbytes, int rank, int world,
                       unsigned int epoch) {
   cross_rank_barrier(peers, rank, world, epoch);
@@ -65,32 +95,21 @@ allreduce_bf16_kernel(unsigned long long mc_base, ArPeers peers, long long offse
   const long long chunks = nbytes / 16 / world;
   const long long first = offset_bytes / 16 + rank * chunks;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < chunks; i += stride) {
-    const long long c = first + i;
-    if (MULTIMEM) {
-      const unsigned long long addr = mc_base + static_cast<unsigned long long>(c) * 16ull;
-      unsigned int x, y, z, w;
-      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(x), "=r"(y), "=r"(z), "=r"(w)
-                   : "l"(addr)
-                   : "memory");
-      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "r"(x), "r"(y), "r"(z), "r"(w)
-                   : "memory");
-    } else {
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int p = 0; p < world; ++p) {
-        float f[8];
-        uint4 v;  // peer (or own) copy through the NVLink mapping: bypass L1, the data was just written by another GPU's kernels
-        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                     : "l"(reinterpret_cast<const uint4*>(peers.buf[p]) + c)
-                     : "memory");
-        unpack8(v, f);
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (MULTIMEM) {
+    const unsigned long long base = mc_base + static_cast<unsigned long long>(first) * 16ull;
+    for (; i + 3 * stride < chunks; i += 4 * stride) {  // 4 independent switch round trips in flight per thread
+      uint4 v[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += f[e];
-      }
-      const uint4 out = pack8(acc);
-      for (int p = 0; p < world; ++p) *(reinterpret_cast<uint4*>(peers.buf[p]) + c) = out;
+      for (int u = 0; u < 4; ++u) v[u] = mm_ld_reduce(base + static_cast<unsigned long long>(i + u * stride) * 16ull);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mm_st(base + static_cast<unsigned long long>(i + u * stride) * 16ull, v[u]);
+    }
+    for (; i < chunks; i += stride) mm_st(base + static_cast<unsigned long long>(i) * 16ull, mm_ld_reduce(base + static_cast<unsigned long long>(i) * 16ull));
+  } else {
+    for (; i < chunks; i += stride) {
+      const uint4 out = p2p_reduce(peers, world, first + i);
+      for (int p = 0; p < world; ++p) *(reinterpret_cast<uint4*>(peers.buf[p]) + first + i) = out;
     }
   }
   __threadfence_system();  // this thread's published chunks are visible system-wide before the flag below is raised
@@ -111,9 +130,9 @@ int allreduce_symm_launch(unsigned long long mc_base, const unsigned long long* 
     peers.pad[i] = i < world ? pad_ptrs[i] : 0ull;
   }
   if (mc_base)
-    allreduce_bf16_kernel<true><<<ctas, 512, 0, st>>>(mc_base, peers, offset_bytes, nbytes, rank, world, epoch);
+    allreduce_bf16_kernel<true><<<ctas, AR_THREADS, 0, st>>>(mc_base, peers, offset_bytes, nbytes, rank, world, epoch);
   else
-    allreduce_bf16_kernel<false><<<ctas, 512, 0, st>>>(0ull, peers, offset_bytes, nbytes, rank, world, epoch);
+    allreduce_bf16_kernel<false><<<ctas, AR_THREADS, 0, st>>>(0ull, peers, offset_bytes, nbytes, rank, world, epoch);
   CB_CUDA_LAUNCH_CHECK("allreduce_bf16");
   return CB_OK;
 }

@@ -143,7 +143,7 @@ class TrainEngine:
             # gradients live in a symmetric allocation every rank maps (and the switch multicasts into): comm.py
             from .comm import SymmetricAllReduce
             import os
-            self._symm = SymmetricAllReduce(total, dev, process_group, ctas=int(os.environ.get("CB_AR_CTAS", "16")),
+            self._symm = SymmetricAllReduce(total, dev, process_group, ctas=int(os.environ.get("CB_AR_CTAS", "0")),
                                             use_multicast=self.collective == "multimem")
             self.flat_g = self._symm.buf
             self._comm_stream = torch.cuda.Stream(device=dev)

@@ -118,7 +118,7 @@ def _symm_worker(rank, world, port, q):
         msgs, ok = [], True
         for use_mc in (True, False):
             n = 8 * world * 4099 * 3
-            ar = SymmetricAllReduce(n, dev, ctas=8, use_multicast=use_mc)
+            ar = SymmetricAllReduce(n, dev, ctas=8 if use_mc else 0, use_multicast=use_mc)
             mode = "multimem" if ar.multicast else "p2p"
             g = torch.Generator(device="cpu").manual_seed(7)
             base = torch.randint(-64, 64, (world, n), generator=g).to(torch.bfloat16)     # exactly representable, exact sums
