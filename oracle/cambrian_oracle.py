@@ -156,7 +156,9 @@ def connector(sd, cfg, tower_feats, aux_masks):
         queries = sd["model.vision_query"][g].view(1, 1, 1, -1).expand(B, qn, -1, -1).flatten(0, 1)
         ctx_g = ctx.expand(-1, qn, 1, -1).flatten(0, 1)
         fw = feats_w if qs == q_side else [window_rearrange(a, qs) for a in aux]
-        gm = aux_masks if qs == q_side else cfg.get("group_masks", {}).get(g)
+        # a group with another side reuses the collator's masks through a raw reshape, exactly as
+        # rearrange_vision_tower_features_train does (cambrian_arch.py:284: `.view(bs * q * q, r * r)`)
+        gm = aux_masks if (qs == q_side or aux_masks is None) else [m.reshape(B * qn, -1) for m in aux_masks]
         qf = sva_sampler(sd, f"model.vision_sampler_{g}.", queries, ctx_g, fw, gm, cfg["connector_depth"]).view(B, qn, -1)
         if qs != q_side:                                                     # :394-401 bilinear resize of the query grid
             t = qf.permute(0, 2, 1).contiguous().view(B, -1, qs, qs)

@@ -480,3 +480,30 @@ def test_cosine_schedule_equals_transformers():
         assert abs(sched.get_last_lr()[0] - f(step)) < 1e-12, step
         opt.step()
         sched.step()
+
+
+def test_module_alias_recipe_from_integration_md():
+    """aliasing `cambrian.model` to the drop-in package must make the reference's import statements
+    resolve to the B200 classes (run in a subprocess: it edits sys.modules)."""
+    import subprocess
+    import sys as _sys
+    code = r'''
+import sys, cambrian_b200.model as m
+sys.modules["cambrian"] = type(sys)("cambrian")
+sys.modules["cambrian.model"] = m
+for sub in ("vision_sampler", "cambrian_arch", "multimodal_encoder.builder", "multimodal_projector.builder",
+            "language_model.cambrian_llama"):
+    sys.modules["cambrian.model." + sub] = __import__("cambrian_b200.model." + sub, fromlist=["*"])
+from cambrian.model.language_model.cambrian_llama import CambrianLlamaForCausalLM, CambrianConfig
+from cambrian.model.vision_sampler import VisionTokenSampler
+from cambrian.model.multimodal_encoder.builder import build_vision_tower_aux_list
+from cambrian.model.multimodal_projector.builder import build_vision_projector
+import cambrian_b200.model.language_model.cambrian_llama as ours
+assert CambrianLlamaForCausalLM is ours.CambrianLlamaForCausalLM and CambrianConfig.model_type == "cambrian_llama"
+from transformers import AutoConfig
+assert type(AutoConfig.for_model("cambrian_llama")).__name__ == "CambrianConfig"
+print("alias ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([_sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=300)
+    assert r.returncode == 0 and "alias ok" in r.stdout, r.stderr[-2000:]

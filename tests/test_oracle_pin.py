@@ -162,6 +162,72 @@ def test_oracle_sva_config1_full_size_against_reference():
 
 
 @needs_ref
+def test_oracle_two_query_groups_static_branch_against_reference():
+    """cambrian_arch.py:382-420 with num_query_group = 2 (a 4x4 and a 2x2 group: own sampler each, window masks reused
+    through the raw reshape of :284, the small group's output bilinearly resized to the final grid :394-401, channel concat,
+    mm_projector, newline column) — the reference's own prepare_inputs_labels_for_multimodal on its static (XLA) branch vs
+    oracle.connector + splice."""
+    import torch.nn as nn
+    vs = ref_shim.ref_module("cambrian.model.vision_sampler")
+    arch = ref_shim.ref_module("cambrian.model.cambrian_arch")
+    H, q, sides, dims = 64, 4, [4, 8], [48, 40]
+
+    class Inner(nn.Module):
+        def __init__(self):
+            super().__init__()
+            for i, c in enumerate(dims):
+                setattr(self, f"mm_projector_aux_{i}", nn.Sequential(nn.Linear(c, 1024), nn.GELU(), nn.Linear(1024, 1024),
+                                                                     nn.LayerNorm(1024)))
+            self.vision_sampler_0 = vs.VisionTokenSampler(1024, 1024, [1024, 1024], [s // 4 for s in sides], 1024, 2)
+            self.vision_sampler_1 = vs.VisionTokenSampler(1024, 1024, [1024, 1024], [s // 2 for s in sides], 1024, 2)
+            self.mm_projector = nn.Sequential(nn.Linear(2048, H), nn.GELU(), nn.Linear(H, H))
+            self.embed_tokens = nn.Embedding(100, H)
+            self.vision_query = nn.Parameter(torch.randn(2, 1024) / 32)
+            self.image_newline = nn.Parameter(torch.randn(H) / 8)
+            self.config = type("C", (), dict(image_token_len=q * q, query_num_list=[q * q, 4], mm_projector_type="sva"))()
+
+        def get_vision_tower_aux_list(self):
+            return [lambda x: x for _ in dims]
+
+    class Top(nn.Module, arch.CambrianMetaForCausalLM):
+        def __init__(self):
+            nn.Module.__init__(self)
+            self.model = Inner()
+            self.config = self.model.config
+            self.device = torch.device("cpu")
+
+        def get_model(self):
+            return self.model
+
+    torch.manual_seed(0)
+    top = Top().eval()
+    B = 2
+    feats = [torch.randn(B, s * s, c) for s, c in zip(sides, dims)]
+    masks = [torch.ones(B * q * q, (s // q) ** 2, dtype=torch.bool) for s in sides]
+    masks[1][::5, 1] = False
+    span = q * (q + 1)
+    ids = torch.randint(3, 100, (B, 5 + span + 6))
+    ids[:, 5] = -200
+    ids[:, 6:5 + span] = 0
+    flag = arch.IS_XLA_AVAILABLE
+    arch.IS_XLA_AVAILABLE = True
+    try:
+        with torch.no_grad():
+            out = top.prepare_inputs_labels_for_multimodal(ids, None, None, None, None, feats, masks, None)
+    finally:
+        arch.IS_XLA_AVAILABLE = flag
+    ref_emb = out[4]
+    sd = {"model." + k: v for k, v in top.model.state_dict().items()}
+    cfg = dict(image_token_len=q * q, query_num_list=[q * q, 4], connector_depth=2)
+    with torch.no_grad():
+        img, feats_w, ctx_q = O.connector(sd, cfg, feats, masks)
+        got = O.splice(sd, ids, img)
+    torch.testing.assert_close(got, ref_emb, rtol=1e-4, atol=2e-5)
+    for a, b in zip(feats_w, out[6]):               # window-rearranged aux features handed to the in-LLM SVA layers
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5)
+
+
+@needs_ref
 def test_oracle_projectors_against_reference():
     pb = ref_shim.ref_module("cambrian.model.multimodal_projector.builder")
     from helpers import ns
