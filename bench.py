@@ -413,6 +413,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL's own tuner picks the LL protocol for the 256 MB gradient buckets on this box (timeline:
+        # ncclDevKernel_AllReduce_Sum_bf16_RING_LL); Simple measured +1 % at N = 8 (profiles/r02_bench_e_n8*.json)
+        os.environ.setdefault("NCCL_PROTO", "Simple")
         dist.init_process_group("nccl", device_id=dev)
     from cambrian_b200 import _lib, ops
     from cambrian_b200.engine import TrainEngine
@@ -620,6 +623,7 @@ def main():
                         "baseline_config": C["baseline_config"], "name": args.config,
                         "micro_batch_per_gpu": B, "global_batch": B * world, "seq_len": S,
                         "parallelism": (f"zero2x{world}" if C["zero"] == 2 else f"dp{world}"),
+                        "collective": engine.collective if world > 1 else None,
                         "activation_recompute": bool(args.recompute),
                         "optimizer": "AdamW fp32 master + bf16 grads, fused, side stream (overlaps the next step's frozen towers)",
                         "grad_clip": engine.max_grad_norm, "trainable_params": n_train, "frozen_tower_params": n_tower,
