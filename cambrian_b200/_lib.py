@@ -73,6 +73,9 @@ SIGNATURES = {
     "cb_preprocess_workspace_bytes": (_i64, [_i, _i, _i]),
     "cb_preprocess_image": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "cb_embed_splice_ragged": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "cb_tower_combine_fwd": (_i, [_vp, _i, _vpp, _vp, _vp, _i64, _i, _i, _vp]),
+    "cb_tower_combine_bwd": (_i, [_vp, _i, _vpp, _vp, _vpp, _vp, _i64, _i, _i, _vp]),
+    "cb_bilinear_bwd": (_i, [_vp, _vp] + [_i] * 6 + [_vp]),
 }
 
 _lib = None

@@ -431,6 +431,178 @@ def _slice_b(D):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# `sep` SVA layer (VisionAggregationLayer.forward, vision_sampler.py:330-405) — building blocks.  The layer type is API
+# surface only (no reference caller constructs it, cambrian_arch.py:60-68 use the default "joint"), so it is composed of
+# finer-grained Functions instead of one hand-scheduled block; every kernel is still one of libcambrian_b200.so.
+# ------------------------------------------------------------------------------------------------------------------
+class CatLinearFn(torch.autograd.Function):
+    """y = cat([a, b], -1) @ W^T without materialising the concatenation (vision_sampler.py:362 + :366 / :370): two GEMMs
+    over the column halves of W accumulate in fp32, rounded to bf16 once."""
+
+    @staticmethod
+    def forward(ctx, a, b, weight):
+        _await(weight)
+        D = a.shape[1]
+        t32 = ops.gemm(a, weight[:, :D], out_dtype=torch.float32)
+        ops.gemm(b, weight[:, D:], out=t32, accumulate=True)
+        y = ops.f32_to_bf16(t32, torch.empty(t32.shape, dtype=torch.bfloat16, device=a.device))
+        ctx.save_for_backward(a, b, weight)
+        ctx.param = weight
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b, weight = ctx.saved_tensors
+        D = a.shape[1]
+        dy = dy.contiguous()
+        da = ops.gemm(dy, weight[:, :D], b_mn=True) if ctx.needs_input_grad[0] else None
+        db = ops.gemm(dy, weight[:, D:], b_mn=True) if ctx.needs_input_grad[1] else None
+        dw = None
+        w_param = ctx.param
+        if ctx.needs_input_grad[2] and not _frozen(w_param):
+            if getattr(w_param, "main_grad", None) is not None:
+                wgrad(w_param, dy, a, out_view=_slice_a(D), notify=False)
+                wgrad(w_param, dy, b, out_view=_slice_b(D))
+            else:
+                dw = torch.cat([ops.gemm(dy, a, a_mn=True, b_mn=True), ops.gemm(dy, b, a_mn=True, b_mn=True)], 1)
+        return da, db, dw
+
+
+class LinearResidualFn(torch.autograd.Function):
+    """y = x @ W^T + residual (residual add in the GEMM epilogue; vision_sampler.py:400-402)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, residual):
+        _await(weight)
+        ctx.save_for_backward(x, weight)
+        ctx.param = weight
+        return ops.gemm(x, weight, residual=residual.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.gemm(dy, weight, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw = wgrad(ctx.param, dy, x) if ctx.needs_input_grad[1] else None
+        return dx, dw, (dy if ctx.needs_input_grad[2] else None)
+
+
+class NarrowLinearFn(torch.autograd.Function):
+    """y[N, 8] = x @ pad8(W)^T for a weight with fewer than 8 output rows (weight_mlp.linear_2: one logit per tower,
+    vision_sampler.py:341,367).  The output keeps the 8-column padding (16-byte rows); columns >= W.shape[0] are zero."""
+
+    PAD = 8
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        _await(weight)
+        T, K = weight.shape
+        if T > NarrowLinearFn.PAD:
+            raise ValueError(f"NarrowLinearFn: {T} output rows > {NarrowLinearFn.PAD}")
+        wpad = torch.zeros((NarrowLinearFn.PAD, K), dtype=weight.dtype, device=weight.device)
+        wpad[:T].copy_(weight)
+        ctx.save_for_backward(x, wpad)
+        ctx.param, ctx.T = weight, T
+        return ops.gemm(x, wpad)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wpad = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.gemm(dy, wpad, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1] and not _frozen(ctx.param):
+            dw = vgrad(ctx.param, ops.gemm(dy, x, a_mn=True, b_mn=True)[:ctx.T].contiguous())
+        return dx, dw
+
+
+class TowerCombineFn(torch.autograd.Function):
+    """q_in + sum_t softmax(logits)[:, t] * agg_t (vision_sampler.py:367-368, :394-396) in one kernel."""
+
+    @staticmethod
+    def forward(ctx, logits, q_in, *aggs):
+        aggs = [a.contiguous() for a in aggs]
+        logits = logits.contiguous()
+        ctx.save_for_backward(logits, *aggs)
+        return ops.tower_combine_fwd(logits, aggs, q_in.contiguous())
+
+    @staticmethod
+    def backward(ctx, dout):
+        logits, *aggs = ctx.saved_tensors
+        dout = dout.contiguous()
+        daggs, dlogits = ops.tower_combine_bwd(logits, aggs, dout)
+        return (dlogits if ctx.needs_input_grad[0] else None, dout, *daggs)
+
+
+class CrossAttnTowerFn(torch.autograd.Function):
+    """AggregationBlock with attention (CrossAttention.forward, vision_sampler.py:79-121) for ONE tower whose window has
+    r^2 > 1 keys: q_proj / k_proj / v_proj = LayerNorm + Linear, window softmax (the SVA kernel with a single tower),
+    o_proj; the layer's pos_embed is added to the latents inside the K/V LayerNorm kernels (:382-387).
+
+    args: meta, q_in [N, 1024], feat (natural [B, (r q)^2, 1024] or windowed [N, r^2, 1024]), then the parameters
+    q_ln_w, q_ln_b, q_w, k_ln_w, k_ln_b, k_w, v_ln_w, v_ln_b, v_w, o_w, pos.
+    meta = dict(r, mask (bool [N, r^2] or None), natural=(B, q_side) or None, params (the 11 nn.Parameters))"""
+
+    NAMES = ("q_ln_w", "q_ln_b", "q_w", "k_ln_w", "k_ln_b", "k_w", "v_ln_w", "v_ln_b", "v_w", "o_w", "pos")
+
+    @staticmethod
+    def forward(ctx, meta, q_in, feat, *tensors):
+        _await(*meta["params"])
+        P = dict(zip(CrossAttnTowerFn.NAMES, tensors))
+        r = meta["r"]
+        N = q_in.shape[0]
+        nat = meta["natural"]
+        windowed = nat is None
+        B, q_side = (N, 1) if windowed else nat
+        side = 0 if windowed else r * q_side
+        masks = None if meta["mask"] is None else [meta["mask"]]
+        f2 = feat.reshape(-1, feat.shape[-1])
+        qn, mq, rq = ops.layernorm_fwd(q_in, P["q_ln_w"], P["q_ln_b"], 1e-5, save_stats=True)
+        Q = ops.gemm(qn, P["q_w"])
+        kin, mean, rstd = ops.layernorm_fwd(f2, P["k_ln_w"], P["k_ln_b"], 1e-5, pos=P["pos"], side=side, r=r, save_stats=True)
+        vin = ops.layernorm_fwd(f2, P["v_ln_w"], P["v_ln_b"], 1e-5, pos=P["pos"], side=side, r=r)
+        K = ops.gemm(kin, P["k_w"])
+        V = ops.gemm(vin, P["v_w"])
+        A, lse = ops.sva_window_attn_fwd(Q, [K], [V], masks, [r], B, q_side, need_lse=True, windowed=windowed)
+        out = ops.gemm(A, P["o_w"])
+        ctx.meta = meta
+        ctx.dims = (N, B, q_side, windowed, side, feat.shape)
+        ctx.save_for_backward(q_in, f2, qn, mq, rq, Q, kin, vin, mean, rstd, K, V, A, lse, *tensors)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        meta = ctx.meta
+        r = meta["r"]
+        N, B, q_side, windowed, side, fshape = ctx.dims
+        sv = ctx.saved_tensors
+        q_in, f2, qn, mq, rq, Q, kin, vin, mean, rstd, K, V, A, lse = sv[:14]
+        P = dict(zip(CrossAttnTowerFn.NAMES, sv[14:]))
+        prm = dict(zip(CrossAttnTowerFn.NAMES, meta["params"]))
+        masks = None if meta["mask"] is None else [meta["mask"]]
+        g = {}
+        dout = dout.contiguous()
+        dA = ops.gemm(dout, P["o_w"], b_mn=True)
+        g["o_w"] = wgrad(prm["o_w"], dout, A)
+        dQ, (dK,), (dV,) = ops.sva_window_attn_bwd(Q, A, dA, lse, [K], [V], masks, [r], B, q_side, windowed=windowed)
+        dqn = ops.gemm(dQ, P["q_w"], b_mn=True)
+        g["q_w"] = wgrad(prm["q_w"], dQ, qn)
+        dq_in, dgq, dbq = ops.layernorm_bwd(dqn, q_in, P["q_ln_w"], mq, rq)
+        g["q_ln_w"], g["q_ln_b"] = vgrad(prm["q_ln_w"], dgq), vgrad(prm["q_ln_b"], dbq)
+        dkin = ops.gemm(dK, P["k_w"], b_mn=True)
+        g["k_w"] = wgrad(prm["k_w"], dK, kin)
+        dvin = ops.gemm(dV, P["v_w"], b_mn=True)
+        g["v_w"] = wgrad(prm["v_w"], dV, vin)
+        dxk, dgk, dbk = ops.layernorm_bwd(dkin, f2, P["k_ln_w"], mean, rstd, pos=P["pos"], side=side, r=r)
+        dxv, dgv, dbv = ops.layernorm_bwd(dvin, f2, P["v_ln_w"], mean, rstd, pos=P["pos"], side=side, r=r, dres=dxk)
+        g["k_ln_w"], g["k_ln_b"] = vgrad(prm["k_ln_w"], dgk), vgrad(prm["k_ln_b"], dbk)
+        g["v_ln_w"], g["v_ln_b"] = vgrad(prm["v_ln_w"], dgv), vgrad(prm["v_ln_b"], dbv)
+        dp = ops.pos_grad(dxv, dxv.shape[0] // (r * r), r, r) if windowed else ops.pos_grad(dxv, B, r * q_side, r)
+        g["pos"] = vgrad(prm["pos"], dp)
+        return (None, dq_in, dxv.view(fshape), *[g[n] for n in CrossAttnTowerFn.NAMES])
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # LLaMA decoder layer (HF LlamaDecoderLayer as called from cambrian_llama.py:142-166)
 # ------------------------------------------------------------------------------------------------------------------
 class DecoderLayerFn(torch.autograd.Function):
@@ -715,18 +887,18 @@ class SpanMergeFn(torch.autograd.Function):
 
 class ResizeTokenGridFn(torch.autograd.Function):
     """cambrian_arch.py:394-401: a query group whose side differs from the final grid is resized with fp32 bilinear
-    interpolation (align_corners=False): [B, q*q, C] -> [B, f*f, C].  Forward only: no released Cambrian-1 recipe uses more
-    than one query group (finetune_cambrian_{8b,13b,34b}.sh: num_query_group 1, query_num_list [576]), so the adjoint
-    kernel has not been written; training through it raises."""
+    interpolation (align_corners=False): [B, q*q, C] -> [B, f*f, C].  Backward = the adjoint gather kernel
+    (`cb_bilinear_bwd`, deterministic)."""
 
     @staticmethod
     def forward(ctx, x, q_side, f_side):
+        ctx.sides = (q_side, f_side)
         return ops.bilinear(x.contiguous(), q_side, q_side, f_side, f_side)
 
     @staticmethod
     def backward(ctx, dy):
-        raise NotImplementedError("backward of the query-grid resize (cambrian_arch.py:394-401) is not implemented: "
-                                  "query groups whose side differs from the final grid are inference-only")
+        q_side, f_side = ctx.sides
+        return ops.bilinear_bwd(dy.contiguous(), q_side, q_side, f_side, f_side), None, None
 
 
 class ExpandRowsFn(torch.autograd.Function):

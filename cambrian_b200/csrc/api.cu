@@ -102,6 +102,10 @@ int preprocess_launch(const uint8_t*, int, int, int, const int*, const float*, c
                       cudaStream_t);
 int window_gather_launch(const void*, void*, int, int, int, int, int, int, int, int, cudaStream_t);
 int embed_splice_ragged_launch(void*, const void*, const void*, const void*, const int*, long long, int, cudaStream_t);
+int tower_combine_fwd_launch(const void*, int, const void* const*, const void*, void*, long long, int, int, cudaStream_t);
+int tower_combine_bwd_launch(const void*, int, const void* const*, const void*, void* const*, void*, long long, int, int,
+                             cudaStream_t);
+int bilinear_bwd_launch(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 
 }  // namespace cb
 
@@ -322,6 +326,17 @@ int cb_sumsq_bf16(const void* g, int64_t n, float* acc, float* workspace, int64_
 }
 int cb_clip_coef(float* sumsq, float max_norm, float inv_world, float* coef, void* stream) {
   return cb::clip_coef_launch(sumsq, max_norm, inv_world, coef, ST(stream));
+}
+int cb_tower_combine_fwd(const void* logits, int ld_logits, const void* const* aggs, const void* q_in, void* out, int64_t N,
+                         int C, int num_towers, void* stream) {
+  return cb::tower_combine_fwd_launch(logits, ld_logits, aggs, q_in, out, N, C, num_towers, ST(stream));
+}
+int cb_tower_combine_bwd(const void* logits, int ld_logits, const void* const* aggs, const void* dout, void* const* daggs,
+                         void* dlogits, int64_t N, int C, int num_towers, void* stream) {
+  return cb::tower_combine_bwd_launch(logits, ld_logits, aggs, dout, daggs, dlogits, N, C, num_towers, ST(stream));
+}
+int cb_bilinear_bwd(const void* dout, void* din, int B, int h, int w, int th, int tw, int C, void* stream) {
+  return cb::bilinear_bwd_launch(dout, din, B, h, w, th, tw, C, ST(stream));
 }
 
 }  // extern "C"

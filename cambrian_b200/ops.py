@@ -443,6 +443,44 @@ def bilinear(x, h: int, w: int, th: int, tw: int, *, in_bs=None, out=None, out_l
     return out
 
 
+def bilinear_bwd(dout, h: int, w: int, th: int, tw: int):
+    """Adjoint of `bilinear` on contiguous grids: dout [B, th*tw, C] -> din [B, h*w, C]."""
+    _require_cuda_bf16(dout)
+    dout = dout.contiguous()
+    B, C_ = dout.shape[0], dout.shape[-1]
+    if dout.shape[1] != th * tw:
+        raise ValueError(f"bilinear_bwd: gradient has {dout.shape[1]} tokens, expected {th} x {tw}")
+    din = torch.empty((B, h * w, C_), dtype=torch.bfloat16, device=dout.device)
+    check(_lib.load().cb_bilinear_bwd(ptr(dout), ptr(din), B, h, w, th, tw, C_, stream()), "cb_bilinear_bwd")
+    return din
+
+
+def tower_combine_fwd(logits, aggs, q_in):
+    """out = q_in + sum_t softmax(logits[:, :T])[:, t] * aggs[t]  (vision_sampler.py:369-371, :396-398).
+    logits [N, >= T] bf16 (extra columns are padding), aggs: T tensors [N, C], q_in [N, C]."""
+    _require_cuda_bf16(logits, q_in, *aggs)
+    N, C_ = q_in.shape
+    if logits.shape[0] != N or logits.stride(1) != 1 or any(a.shape != q_in.shape or not a.is_contiguous() for a in aggs):
+        raise ValueError("tower_combine_fwd: logits [N, Tpad] and T contiguous aggregates shaped like q_in are required")
+    out = torch.empty_like(q_in)
+    check(_lib.load().cb_tower_combine_fwd(ptr(logits), logits.stride(0), ptr_array(aggs), ptr(q_in), ptr(out), N, C_,
+                                           len(aggs), stream()), "cb_tower_combine_fwd")
+    return out
+
+
+def tower_combine_bwd(logits, aggs, dout):
+    """Returns (daggs: list of T [N, C], dlogits [N, Tpad] with zero padding columns); d q_in is dout itself."""
+    _require_cuda_bf16(logits, dout, *aggs)
+    N, C_ = dout.shape
+    if not logits.is_contiguous() or not dout.is_contiguous():
+        raise ValueError("tower_combine_bwd: contiguous logits / dout are required")
+    daggs = [torch.empty_like(a) for a in aggs]
+    dlogits = torch.empty_like(logits)
+    check(_lib.load().cb_tower_combine_bwd(ptr(logits), logits.stride(0), ptr_array(aggs), ptr(dout), ptr_array(daggs),
+                                           ptr(dlogits), N, C_, len(aggs), stream()), "cb_tower_combine_bwd")
+    return daggs, dlogits
+
+
 def patchify_nchw(img, p: int):
     B, Cin, R, _ = img.shape
     img = img.contiguous()

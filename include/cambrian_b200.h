@@ -240,6 +240,19 @@ int cb_sumsq_bf16(const void* g, int64_t n, float* acc, float* workspace, int64_
 /* coef[0] = inv_world * min(1, max_norm / (sqrt(sumsq[0]) * inv_world + 1e-6)); coef[1] = that norm; sumsq[0] = 0
  * (torch.nn.utils.clip_grad_norm_ on the rank-averaged gradient, all on the device) */
 int cb_clip_coef(float* sumsq, float max_norm, float inv_world, float* coef, void* stream);
+/* `sep` aggregator layer (VisionAggregationLayer.forward, vision_sampler.py:368-398): per-query softmax over the towers
+ * of the weight_mlp logits and the weighted sum of the per-tower aggregates added to the query stream,
+ *   out[n,:] = q_in[n,:] + sum_t softmax(logits[n,:T])[t] * aggs[t][n,:]        (replaces .softmax(-1), torch.stack,
+ * (agg * weight).sum(2) and the residual add).  logits [N, ld_logits >= T] bf16 (columns >= T are padding), aggs = HOST
+ * array of T device pointers to [N, C] bf16.  Backward: daggs[t] = w_t * dout, dlogits = softmax adjoint of
+ * g_t = <dout, agg_t> (padding columns zeroed); d q_in = dout. */
+int cb_tower_combine_fwd(const void* logits, int ld_logits, const void* const* aggs, const void* q_in, void* out, int64_t N,
+                         int C, int num_towers, void* stream);
+int cb_tower_combine_bwd(const void* logits, int ld_logits, const void* const* aggs, const void* dout, void* const* daggs,
+                         void* dlogits, int64_t N, int C, int num_towers, void* stream);
+/* adjoint of cb_bilinear on contiguous grids: dout [B, th, tw, C] -> din [B, h, w, C] (backward of the query-grid resize
+ * cambrian_arch.py:394-401 and of the towers' token interpolation, clip_encoder.py:83-88 and siblings); deterministic */
+int cb_bilinear_bwd(const void* dout, void* din, int B, int h, int w, int th, int tw, int C, void* stream);
 
 #ifdef __cplusplus
 }

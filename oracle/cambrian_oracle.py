@@ -118,10 +118,52 @@ def sva_layer(sd, p, queries, ctx, feats, masks, heads=16):
     return q + residual                                                     # :325
 
 
-def sva_sampler(sd, p, queries, ctx, feats, masks, num_layers):
-    """VisionTokenSampler.forward, vision_sampler.py:416-419."""
+def sva_agg_layer(sd, p, queries, ctx, feats, masks, heads=16):
+    """VisionAggregationLayer.forward (layer_type="sep"), vision_sampler.py:330-405: one aggregate per tower —
+    CrossAttention (:55-121) over the r_i^2 window when r_i > 1, a two-layer MLP of the single latent otherwise
+    (AggregationBlock :124-153) — mixed with a per-query softmax over towers (weight_mlp, :369-371) and added to the
+    query stream (:396-398)."""
+    n = queries.shape[0]
+    T = len(feats)
+    residual = queries
+    c = F.linear(ctx, sd[p + "proj_context.weight"])                                    # :360
+    cat = torch.cat([queries, c], -1)                                                    # :362
+    if T > 1:                                                                            # :364-368
+        w = F.linear(F.gelu(F.linear(cat, sd[p + "weight_mlp.linear_1.weight"])), sd[p + "weight_mlp.linear_2.weight"])
+        w = w.softmax(-1).unsqueeze(-1)                                                  # [N, 1, T, 1]
+    else:
+        w = 1
+    q = F.linear(cat, sd[p + "proj_in.weight"])                                          # :370
+    hidden = q.shape[-1]
+    hd = hidden // heads
+    aggs = []
+    for i, f in enumerate(feats):
+        a = p + f"aggregate_{i}.attention_layer."
+        if f.shape[1] > 1:                                                               # :382-387, CrossAttention :79-121
+            f = f + sd[p + f"pos_embed_{i}"][None].to(f.dtype)
+            Q = _lin(sd, a + "q_proj.1", _ln(sd, a + "q_proj.0", q), bias=False).view(n, 1, heads, hd).transpose(1, 2)
+            K = _lin(sd, a + "k_proj.1", _ln(sd, a + "k_proj.0", f), bias=False).view(n, -1, heads, hd).transpose(1, 2)
+            V = _lin(sd, a + "v_proj.1", _ln(sd, a + "v_proj.0", f), bias=False).view(n, -1, heads, hd).transpose(1, 2)
+            s_ = (Q @ K.transpose(-1, -2)) / math.sqrt(hd)
+            m = masks[i] if masks is not None and masks[i] is not None else None
+            if m is not None:
+                s_ = s_.masked_fill(~m.view(n, 1, 1, -1).bool().to(f.device), float("-inf"))
+            o = (torch.softmax(s_, -1) @ V).transpose(1, 2).reshape(n, 1, hidden)
+            aggs.append(F.linear(o, sd[a + "o_proj.weight"]))
+        else:                                                                            # MLP(kv_dim, q_dim, q_dim) :140
+            aggs.append(F.linear(F.gelu(F.linear(f, sd[a + "linear_1.weight"])), sd[a + "linear_2.weight"]))
+    agg = torch.stack(aggs, 2)                                                           # :394  [N, 1, T, hidden]
+    q = q + (agg * w).sum(2)                                                             # :396
+    q = _ln(sd, p + "norm", q)                                                           # :398
+    q = F.linear(F.gelu(F.linear(q, sd[p + "proj_out.linear_1.weight"])), sd[p + "proj_out.linear_2.weight"])
+    return q + residual                                                                  # :402
+
+
+def sva_sampler(sd, p, queries, ctx, feats, masks, num_layers, layer_type="joint"):
+    """VisionTokenSampler.forward, vision_sampler.py:407-419."""
+    layer = sva_layer if layer_type == "joint" else sva_agg_layer
     for l in range(num_layers):
-        queries = sva_layer(sd, f"{p}layers.{l}.", queries, ctx, feats, masks)
+        queries = layer(sd, f"{p}layers.{l}.", queries, ctx, feats, masks)
     return queries
 
 

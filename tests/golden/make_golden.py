@@ -7,7 +7,7 @@ Weights are not stored: every parameter is regenerated from numpy's PCG64 stream
 `seeded_fill`, in state-dict order, so the fixtures stay a few hundred KB.  Each .npz holds the seeded inputs and the
 reference's outputs for:
   sva_*.npz        VisionTokenSampler.forward (vision_sampler.py:407-419) — connector shape (q_dim 1024) and in-LLM
-                   shape (q_dim 256), kv sizes with r > 1 and letter-box style masks
+                   shape (q_dim 256), kv sizes with r > 1 and letter-box style masks; sva_sep*.npz: layer_type="sep"
   rearrange.npz    rearrange_vision_tower_features_train (cambrian_arch.py:271-287)
   collator.npz     prepare_image_info / get_padding_offset (train_fsdp.py:1039-1085) for several image sizes
   dynamic.npz      the off-XLA (inference) branch for non-square images: unmask_attention_mask / unpad_image /
@@ -73,6 +73,13 @@ SVA_FULL_CASES = {
     "sva_config1": dict(q_dim=1024, rs=[1, 1, 1, 1], layers=3, n=576, seed=51),
     "sva_config1_r4": dict(q_dim=1024, rs=[1, 1, 1, 4], layers=3, n=576, seed=52),
     "sva_inllm_4096": dict(q_dim=4096, rs=[1, 1, 1, 4], layers=1, n=576, seed=53),
+}
+
+# layer_type="sep" (VisionAggregationLayer, vision_sampler.py:330-405): API surface no reference caller constructs; one
+# case with attention towers (r > 1), MLP towers (r = 1) and masks, one single-tower case (no weight_mlp)
+SVA_SEP_CASES = {
+    "sva_sep": dict(q_dim=256, rs=[2, 1, 3, 1], layers=2, n=24, seed=61),
+    "sva_sep_single": dict(q_dim=1024, rs=[2], layers=1, n=16, seed=62),
 }
 
 DYN = dict(sizes=[(800, 400), (336, 336), (200, 500)], q=4, tower_dims=[96, 80], tower_sides=[4, 8], H=128, vocab=200,
@@ -181,14 +188,33 @@ def make_full(vs):
         print(name, tuple(out.shape), float(out.abs().mean()))
 
 
+def make_sep(vs):
+    for name, c in SVA_SEP_CASES.items():
+        T = len(c["rs"])
+        m = vs.VisionTokenSampler(c["q_dim"], 1024, [1024] * T, c["rs"], 1024, c["layers"], layer_type="sep").eval()
+        sd = seeded_fill(m, c["seed"])
+        m.load_state_dict(sd)
+        queries, ctx, feats, masks = seeded_inputs(c["seed"] + 100, c["n"], c["q_dim"], c["rs"])
+        with torch.no_grad():
+            out = m(queries, ctx, *feats, *masks)
+        # parameter names / shapes in state-dict order, so the tests regenerate the weights without the reference
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), out=out.numpy(), sd_keys=np.array(list(sd.keys())),
+                            sd_shapes=np.array([",".join(map(str, v.shape)) for v in sd.values()]))
+        print(name, tuple(out.shape), float(out.abs().mean()))
+
+
 def main():
     from oracle import ref_shim
     vs = ref_shim.ref_module("cambrian.model.vision_sampler")
+    if "--only-sep" in sys.argv:
+        make_sep(vs)
+        return
     arch = ref_shim.ref_module("cambrian.model.cambrian_arch")
     if "--only-full" in sys.argv:
         make_full(vs)
         return
     make_full(vs)
+    make_sep(vs)
     for name, c in SVA_CASES.items():
         T = len(c["rs"])
         m = vs.VisionTokenSampler(c["q_dim"], 1024, [1024] * T, c["rs"], 1024, c["layers"]).eval()

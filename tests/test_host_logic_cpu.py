@@ -92,11 +92,33 @@ def test_projector_builder_keys_and_errors():
 def test_sampler_rejects_unsupported_configs():
     from cambrian_b200.model.vision_sampler import VisionTokenSampler
     with pytest.raises(NotImplementedError):
-        VisionTokenSampler(64, 1024, [1024], [1], 1024, 1, layer_type="sep")
-    with pytest.raises(NotImplementedError):
         VisionTokenSampler(64, 512, [512], [1], 512, 1)
+    with pytest.raises(NotImplementedError):
+        VisionTokenSampler(64, 512, [512], [1], 512, 1, layer_type="sep")
     with pytest.raises(AssertionError):
         VisionTokenSampler(64, 1024, [1024], [1], 1024, 1, layer_type="bogus")
+
+
+def test_sep_sampler_state_dict_follows_the_reference_layout():
+    """layer_type="sep" (VisionAggregationLayer, vision_sampler.py:330-405): parameter names and shapes in registration
+    order — weight_mlp only with more than one tower, CrossAttention for r > 1, an MLP otherwise; CPU tensors raise."""
+    from cambrian_b200.model.vision_sampler import VisionTokenSampler
+    from oracle import ref_shim
+    m = VisionTokenSampler(256, 1024, [1024] * 3, [2, 1, 3], 1024, 2, layer_type="sep")
+    sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    p = "layers.1."
+    assert sd[p + "weight_mlp.linear_2.weight"] == (3, 1024) and sd[p + "weight_mlp.linear_1.weight"] == (1024, 1280)
+    assert sd[p + "aggregate_0.attention_layer.q_proj.0.bias"] == (1024,) and sd[p + "pos_embed_2"] == (9, 1024)
+    assert sd[p + "aggregate_1.attention_layer.linear_1.weight"] == (1024, 1024) and p + "pos_embed_1" not in sd
+    single = VisionTokenSampler(256, 1024, [1024], [2], 1024, 1, layer_type="sep")
+    assert not any("weight_mlp" in k for k in single.state_dict())
+    if ref_shim.available():
+        vs = ref_shim.ref_module("cambrian.model.vision_sampler")
+        r = vs.VisionTokenSampler(256, 1024, [1024] * 3, [2, 1, 3], 1024, 2, layer_type="sep")
+        assert list(sd.items()) == [(k, tuple(v.shape)) for k, v in r.state_dict().items()]
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(4, 1, 256), torch.zeros(4, 1, 1024), torch.zeros(4, 4, 1024), torch.zeros(4, 1, 1024),
+          torch.zeros(4, 9, 1024))
 
 
 # ------------------------------------------------------------------------------------------------ model plumbing

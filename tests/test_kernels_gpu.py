@@ -142,3 +142,61 @@ def test_process_images_returns_one_tensor_per_tower():
     outs = process_images(imgs, procs)
     assert [tuple(o.shape) for o in outs] == [(2, 3, 384, 384), (2, 3, 336, 336)]
     assert all(o.dtype == torch.bfloat16 and o.is_cuda and torch.isfinite(o.float()).all() for o in outs)
+
+
+@pytest.mark.parametrize("h,th,C", [(2, 4, 256), (12, 24, 1024), (24, 12, 1024), (27, 24, 1152), (5, 3, 64)])
+def test_bilinear_backward_is_the_adjoint_of_the_forward(h, th, C):
+    """cb_bilinear_bwd (the query-grid resize of cambrian_arch.py:394-401 under training) vs torch autograd through
+    F.interpolate(bilinear, align_corners=False), and <bilinear(x), g> == <x, bilinear_bwd(g)> on the kernels themselves."""
+    import torch
+    import torch.nn.functional as F
+    from cambrian_b200 import ops
+    torch.manual_seed(0)
+    B = 2
+    x = torch.randn(B, h * h, C, device="cuda").bfloat16()
+    g = torch.randn(B, th * th, C, device="cuda").bfloat16()
+    xf = x.float().view(B, h, h, C).permute(0, 3, 1, 2).requires_grad_()
+    y = F.interpolate(xf, size=(th, th), mode="bilinear", align_corners=False)
+    (gx,) = torch.autograd.grad(y, xf, g.float().view(B, th, th, C).permute(0, 3, 1, 2))
+    ref = gx.permute(0, 2, 3, 1).reshape(B, h * h, C)
+    got = ops.bilinear_bwd(g, h, h, th, th)
+    torch.cuda.synchronize()
+    err = ((got.float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 6e-3, err           # one bf16 rounding of the fp32 sum
+    fwd = ops.bilinear(x, h, h, th, th)
+    lhs, rhs = (fwd.float() * g.float()).sum().item(), (x.float() * got.float()).sum().item()
+    assert abs(lhs - rhs) <= 2e-2 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+
+
+@pytest.mark.parametrize("T,N,C", [(1, 37, 1024), (4, 300, 1024), (8, 64, 256)])
+def test_tower_combine_forward_backward(T, N, C):
+    """cb_tower_combine_fwd / _bwd (softmax over towers + weighted sum + residual, vision_sampler.py:367-368, :394-396) vs
+    fp32 torch autograd."""
+    import torch
+    from cambrian_b200 import ops
+    torch.manual_seed(0)
+    logits = torch.zeros(N, 8, device="cuda").bfloat16()
+    logits[:, :T] = (torch.randn(N, T, device="cuda") * 2).bfloat16()
+    aggs = [torch.randn(N, C, device="cuda").bfloat16() for _ in range(T)]
+    qin = torch.randn(N, C, device="cuda").bfloat16()
+    dout = torch.randn(N, C, device="cuda").bfloat16()
+    lf = logits.float()[:, :T].clone().requires_grad_()
+    af = [a.float().requires_grad_() for a in aggs]
+    w = torch.softmax(lf, -1)
+    ref = qin.float() + sum(w[:, t:t + 1] * af[t] for t in range(T))
+    grads = torch.autograd.grad(ref, [lf, *af], dout.float())
+    out = ops.tower_combine_fwd(logits, aggs, qin)
+    daggs, dlogits = ops.tower_combine_bwd(logits, aggs, dout)
+    torch.cuda.synchronize()
+
+    def e(a, b):
+        return ((a.float() - b).abs().max() / (b.abs().max() + 1e-6)).item()
+
+    assert e(out, ref) < 6e-3, e(out, ref)
+    for t in range(T):
+        assert e(daggs[t], grads[1 + t]) < 6e-3, (t, e(daggs[t], grads[1 + t]))
+    if T > 1:
+        assert e(dlogits[:, :T], grads[0]) < 1e-2, e(dlogits[:, :T], grads[0])
+    else:
+        assert float(dlogits.float().abs().max()) < 1e-3
+    assert float(dlogits[:, T:].float().abs().max()) == 0.0 if T < 8 else True

@@ -12,7 +12,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from make_golden import SVA_CASES, SVA_FULL_CASES, seeded_fill, seeded_inputs  # noqa: E402
+from make_golden import SVA_CASES, SVA_FULL_CASES, SVA_SEP_CASES, seeded_fill, seeded_inputs  # noqa: E402
 
 from oracle import cambrian_oracle as O  # noqa: E402
 from oracle import ref_shim  # noqa: E402
@@ -52,6 +52,48 @@ def test_sva_oracle_matches_reference_golden(name):
         got = O.sva_sampler(sd, "", queries, ctx, feats, masks, c["layers"])
     ref = torch.from_numpy(np.load(os.path.join(GOLD, name + ".npz"))["out"])
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
+
+
+def _sep_state_dict(name):
+    """Seeded weights of a layer_type="sep" sampler, regenerated from the parameter names / shapes stored in the golden."""
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    shapes = {str(k): tuple(int(x) for x in str(sh).split(",")) for k, sh in zip(z["sd_keys"], z["sd_shapes"])}
+    return seeded_fill({k: torch.empty(v) for k, v in shapes.items()}, SVA_SEP_CASES[name]["seed"]), z
+
+
+@pytest.mark.parametrize("name", sorted(SVA_SEP_CASES))
+def test_sva_sep_oracle_matches_reference_golden(name):
+    """VisionAggregationLayer restatement (oracle.sva_agg_layer) vs the committed output of the reference's own
+    VisionTokenSampler(layer_type="sep") (vision_sampler.py:330-419)."""
+    c = SVA_SEP_CASES[name]
+    sd, z = _sep_state_dict(name)
+    queries, ctx, feats, masks = seeded_inputs(c["seed"] + 100, c["n"], c["q_dim"], c["rs"])
+    with torch.no_grad():
+        got = O.sva_sampler(sd, "", queries, ctx, feats, masks, c["layers"], layer_type="sep")
+    torch.testing.assert_close(got, torch.from_numpy(z["out"]), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("rs,q_dim,layers", [([1, 2, 1], 256, 2), ([3], 512, 1), ([1], 1024, 1)])
+def test_sva_sep_oracle_matches_live_reference_fwd_bwd(rs, q_dim, layers):
+    """Output AND gradients of the sep restatement against the live reference module."""
+    vs = ref_shim.ref_module("cambrian.model.vision_sampler")
+    T = len(rs)
+    m = vs.VisionTokenSampler(q_dim, 1024, [1024] * T, rs, 1024, layers, layer_type="sep")
+    m.load_state_dict(seeded_fill(m, 71))
+    queries, ctx, feats, masks = seeded_inputs(72, 10, q_dim, rs)
+    queries.requires_grad_()
+    ref = m(queries, ctx, *feats, *masks)
+    dy = torch.randn_like(ref)
+    names = [k for k, _ in m.named_parameters()]
+    gref = torch.autograd.grad(ref, [queries] + [p for _, p in m.named_parameters()], dy)
+    sd = {k: v.detach().clone().requires_grad_() for k, v in m.state_dict().items()}
+    q2 = queries.detach().clone().requires_grad_()
+    got = O.sva_sampler(sd, "", q2, ctx, feats, masks, layers, layer_type="sep")
+    ggot = torch.autograd.grad(got, [q2] + [sd[k] for k in names], dy)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5)
+    for a, b, k in zip(ggot, gref, ["queries"] + names):
+        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5, msg=lambda s_, k=k: f"{k}: {s_}")
 
 
 @pytest.mark.parametrize("name", sorted(SVA_FULL_CASES))

@@ -23,8 +23,8 @@ from helpers import (FP32_RTOL, ParityCollector, bf, both_modes, ns, oracle_cfg,
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from make_golden import SVA_CASES, SVA_FULL_CASES, seeded_fill, seeded_inputs  # noqa: E402
-from test_oracle_pin import _sva_shapes  # noqa: E402
+from make_golden import SVA_CASES, SVA_FULL_CASES, SVA_SEP_CASES, seeded_fill, seeded_inputs  # noqa: E402
+from test_oracle_pin import _sep_state_dict, _sva_shapes  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 dev = "cuda"
@@ -73,6 +73,32 @@ def test_reference_golden_through_cuda_sampler(name):
         torch.testing.assert_close(ref32.cpu(), gold, rtol=1e-3, atol=1e-4)
     pc.check(got, ref32, eager, f"golden {name}: vs fp32 oracle")
     pc.done()
+
+
+@pytest.mark.parametrize("name", sorted(SVA_SEP_CASES))
+def test_reference_sep_golden_through_cuda_sampler(name):
+    """layer_type="sep": the committed output of the reference's VisionTokenSampler(..., layer_type="sep") vs the CUDA module
+    called with the reference convention (window-rearranged latents + bool masks)."""
+    from cambrian_b200.model.vision_sampler import VisionTokenSampler
+    from oracle import cambrian_oracle as O
+    c = SVA_SEP_CASES[name]
+    T = len(c["rs"])
+    sd, z = _sep_state_dict(name)
+    queries, ctx, feats, masks = seeded_inputs(c["seed"] + 100, c["n"], c["q_dim"], c["rs"])
+    m = VisionTokenSampler(c["q_dim"], 1024, [1024] * T, c["rs"], 1024, c["layers"], layer_type="sep")
+    m.load_state_dict(sd)
+    m = m.to(device=dev, dtype=torch.bfloat16)
+    with torch.no_grad():
+        got = m(queries.to(dev).bfloat16(), ctx.to(dev).bfloat16(), *[f.to(dev).bfloat16() for f in feats],
+                *[k.to(dev) for k in masks]).float()[:, 0]
+        ref32, eager = _both(lambda s, q, cx, *fm: O.sva_sampler(s, "", q, cx, list(fm[:T]), list(fm[T:]), c["layers"],
+                                                                  layer_type="sep"), sd, queries, ctx, *feats, *masks)
+    gold = torch.from_numpy(z["out"])[:, 0]
+    pc = ParityCollector()
+    pc.check(got, gold, eager[:, 0], f"golden {name}: vs reference output")
+    pc.check(got, ref32[:, 0], eager[:, 0], f"golden {name}: vs fp32 oracle")
+    pc.done()
+    torch.testing.assert_close(ref32[:, 0].cpu(), gold, rtol=1e-3, atol=1e-4)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -423,7 +449,7 @@ def test_greedy_generate_token_exact_32_tokens():
 def test_two_query_groups_with_grid_resize_match_oracle():
     """cambrian_arch.py:382-402 with num_query_group = 2: a 4x4 and a 2x2 query group, each with its own sampler and kv
     window sizes; the 2x2 group's output is bilinearly resized to the final 4x4 grid (:394-401) and channel-concatenated
-    before mm_projector.  Inference (the resize has no backward here)."""
+    before mm_projector.  Inference; the training step through the resize is the next test."""
     from test_modules_gpu import _build_tiny_model, _tiny_batch, _tower_fn, TOWER_KINDS
     from oracle import cambrian_oracle as O
     cfg = tiny_cambrian_config()
@@ -457,4 +483,34 @@ def test_two_query_groups_with_grid_resize_match_oracle():
     valid = attn.to(dev)
     pc = ParityCollector()
     pc.check(out.logits[valid], ref[valid], eag[valid], "two query groups (16 + 4 -> resize): logits")
+    pc.done()
+
+
+def test_two_query_groups_train_step_matches_oracle():
+    """Training through the query-grid resize (cambrian_arch.py:394-401): loss and every parameter gradient of the
+    two-group model (4x4 + 2x2 -> bilinear -> 4x4) vs the oracle; the adjoint of the resize is cb_bilinear_bwd."""
+    from test_modules_gpu import _build_tiny_model, _tiny_batch, oracle_full_model_both
+    cfg = tiny_cambrian_config()
+    cfg.num_query_group = 2
+    cfg.query_num_list = [16, 4]
+    model = _build_tiny_model(cfg)
+    model.train()
+    ids, labels, attn, pos, images, _ = _tiny_batch(cfg)
+    (_, ref_loss, gref), (_, eag_loss, geag) = oracle_full_model_both(model, cfg, ids, labels, attn, pos, images, None)
+    out = model(input_ids=ids.to(dev), labels=labels.to(dev), attention_mask=attn.to(dev), position_ids=pos.to(dev),
+                images=[i.to(dev).bfloat16() for i in images])
+    out.loss.backward()
+    lim = max(FP32_RTOL * abs(ref_loss.item()), 1.5 * abs(eag_loss.item() - ref_loss.item()))
+    assert abs(out.loss.item() - ref_loss.item()) <= lim, (out.loss.item(), ref_loss.item(), eag_loss.item())
+    pc = ParityCollector()
+    seen_group1 = False
+    for k, p in model.named_parameters():
+        g = gref[k]
+        if g is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, f"missing grad for {k}"
+        seen_group1 = seen_group1 or "vision_sampler_1." in k
+        pc.check(p.grad, g, geag[k], f"two query groups (train): grad {k}")
+    assert seen_group1, "the resized group's sampler received no gradient"
     pc.done()
