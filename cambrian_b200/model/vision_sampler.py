@@ -16,6 +16,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .. import ops
 from ..autograd import (ActFn, CatLinearFn, CrossAttnTowerFn, LayerNormFn, LinearFn, LinearResidualFn, NarrowLinearFn,
                         SVALayerFn, TowerCombineFn)
 
@@ -103,9 +104,7 @@ class VisionCrossAttentionLayer(nn.Module):
         items = self._named_params()
         names = [k for k, _ in items]
         params = [p for _, p in items]
-        if any(p.dtype != torch.bfloat16 or not p.is_cuda for p in params):
-            raise RuntimeError("cambrian_b200 SVA layers run in bf16 on CUDA only (no CPU / fp32 fallback): "
-                               "call .to(device='cuda', dtype=torch.bfloat16)")
+        ops.require_cuda_bf16_params(params, "SVA layers")
         meta = dict(T=T, rs=self.kv_size_list, masks=masks, natural=natural_layout, names=names, params=params,
                     feat_shapes=[t.shape for t in latents])
         q2 = queries.reshape(n, -1)
@@ -188,9 +187,7 @@ class VisionAggregationLayer(nn.Module):
             if m is not None and m.numel() != n * self.kv_size_list[i] ** 2:
                 raise ValueError(f"Attention mask should be of size {(n, 1, 1, self.kv_size_list[i] ** 2)}, "
                                  f"but is {tuple(m.shape)}")
-        if any(p.dtype != torch.bfloat16 or not p.is_cuda for p in self.parameters()):
-            raise RuntimeError("cambrian_b200 SVA layers run in bf16 on CUDA only (no CPU / fp32 fallback): "
-                               "call .to(device='cuda', dtype=torch.bfloat16)")
+        ops.require_cuda_bf16_params(list(self.parameters()), "SVA layers")
         q2 = queries.reshape(n, -1).contiguous()
         c2 = context_feature.reshape(n, -1).contiguous()
         ctxp = LinearFn.apply(c2, self.proj_context.weight, None)                                  # :360

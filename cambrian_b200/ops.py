@@ -61,6 +61,13 @@ def _require_cuda_bf16(*ts):
             raise ValueError(f"expected bf16 tensor, got {t.dtype}")
 
 
+def require_cuda_bf16_params(params, what: str):
+    """Module-level guard: every parameter must already live on the GPU in bf16 (there is no CPU / fp32 fallback)."""
+    if any(p.dtype != torch.bfloat16 or not p.is_cuda for p in params):
+        raise RuntimeError(f"cambrian_b200 {what} run in bf16 on CUDA only (no CPU / fp32 fallback): "
+                           "call .to(device='cuda', dtype=torch.bfloat16)")
+
+
 def _chk(t, name):
     _require_cuda_bf16(t)
     if not t.is_contiguous():
