@@ -4,6 +4,7 @@
     python bench.py --gpus N --steps K --warmup W                    # this framework (hand-written sm_100a kernels)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host cores
     python bench.py --config {8b-ddp,7b-clip-mlp,13b-zero2} ...      # BASELINE.json configs 3 (default), 2, 4
+    python bench.py --config 8b-release                              # the released 8B recipe's towers / grids (not a BASELINE config)
 
 Workloads:
   8b-ddp       config 3 — Llama-3-8B decoder (32 L, H 4096, 32/8 heads x 128, FFN 14336, vocab 128256), four towers
@@ -14,6 +15,10 @@ Workloads:
                (32 L, H 4096, 32 heads x 128, FFN 11008, vocab 32000), seq 1024, no SVA anywhere.
   13b-zero2    config 4 — Vicuna-13B-shaped decoder (40 L, H 5120, 40 heads, FFN 13824), 4 towers, SVA (stride 4),
                ZeRO-2: per-bucket reduce-scatter, sharded fp32 master / Adam state, in-place all-gather (needs >= 2 GPUs).
+  8b-release   the released Cambrian-1-8B recipe (scripts/cambrian/finetune_cambrian_8b.sh:17-29): DINOv2-giant@378 (SwiGLU
+               FFN) instead of ViT-L, ConvNeXt-XXL multi-stage (4 stages -> 96 x 96 x 5760 = 9216 tokens), SVA grids
+               [576, 576, 576, 9216] (16-key windows on the ConvNeXt grid, learned pos_embed), per-layer activation
+               recompute as the recipe's `--gradient_checkpointing True`.  Not a BASELINE.json config: no CPU arm.
 All: bf16 compute with fp32 master weights + AdamW (lr 4e-5, wd 0) and gradient clipping at max_grad_norm 1.0 (HF
 Trainer's default, active in every reference script), random-init weights, synthetic images / ids (no network).
 One "step" = towers fwd + (connector + decoder + loss) fwd/bwd + gradient collective + clip + AdamW on one micro-batch per
@@ -40,6 +45,7 @@ UNIT = "samples/s"
 
 # algorithmic forward TFLOP per sample of the frozen towers
 TOWER_TF = {"siglip": 0.665, "clip": 0.381, "dino": 0.381, "convnext1024": 6.335}
+TOWER_TF_RELEASE = {"siglip": 0.665, "clip": 0.381, "dino_giant378": 1.78, "convnext1024": 6.335}   # SURVEY.md §8d deltas
 
 LLMS = {
     "llama3-8b": dict(hidden_size=4096, intermediate_size=14336, num_hidden_layers=32, num_attention_heads=32,
@@ -57,7 +63,15 @@ LLMS = {
 }
 FOUR_TOWERS = ["siglip/CLIP-ViT-SO400M-14-384", "openai/clip-vit-large-patch14-336", "facebook/dinov2-large-res336",
                "clip-convnext-XXL"]
+RELEASE_TOWERS = ["siglip/CLIP-ViT-SO400M-14-384", "openai/clip-vit-large-patch14-336", "facebook/dinov2-giant-res378",
+                  "clip-convnext-XXL-multi-stage"]
 CONFIGS = {
+    "8b-release": dict(llm="llama3-8b", towers=RELEASE_TOWERS, res=[384, 336, 378, 1024], token_lens=[576, 576, 576, 9216],
+                       sva=True, stride=3, n_sva=10, image_position=91, seq=2048, micro_batch=4, zero=0, recompute=1,
+                       baseline_config=None, tower_tf=sum(TOWER_TF_RELEASE.values()), aux_tf=0.136,
+                       workload="Cambrian-1-8B RELEASE recipe train step (finetune_cambrian_8b.sh): SigLIP-SO400M@384, CLIP-L@336, "
+                                "DINOv2-giant@378, ConvNeXt-XXL@1024 multi-stage -> SVA grids [576,576,576,9216] (3 + 10 layers) "
+                                "-> Llama-3-8B, 576 vis-tok, seq 2048, per-layer recompute"),
     "8b-ddp": dict(llm="llama3-8b", towers=FOUR_TOWERS, res=[384, 336, 336, 1024], sva=True, stride=3, n_sva=10,
                    image_position=91, seq=2048, micro_batch=4, zero=0, baseline_config=3,
                    tower_tf=sum(TOWER_TF.values()),
@@ -80,7 +94,7 @@ def build_config(name, small=False):
     c = CONFIGS[name]
     cfg = CambrianConfig(**LLMS["small" if small else c["llm"]])
     cfg.mm_vision_tower_aux_list = list(c["towers"])
-    cfg.mm_vision_tower_aux_token_len_list = [576] * len(c["towers"])
+    cfg.mm_vision_tower_aux_token_len_list = list(c.get("token_lens", [576] * len(c["towers"])))
     cfg.image_token_len = 576
     cfg.image_position = c["image_position"]
     cfg.fused_lm_loss = True
@@ -114,18 +128,19 @@ def llm_fwd_tflop(cfg, S):
     return S * (lin + attn) / 1e12
 
 
-def sva_fwd_tflop(cfg, T):
-    """SVA connector + in-LLM layers + aux projectors + mm_projector, 576 queries, T grids of 576 x 1024 (BASELINE.md §2:
-    0.308 + 0.012 + 0.024 for the 8B config)."""
+def sva_fwd_tflop(cfg, T, aux_tf=None):
+    """SVA connector + in-LLM layers + aux projectors + mm_projector, 576 queries over the towers' grids (BASELINE.md §2:
+    0.308 + 0.012 + 0.024 for the 8B config with four 576-token grids; 0.780 + 0.136 for the release grids)."""
     if cfg.mm_projector_type != "sva":
         return 576 * (2 * 1024 * cfg.hidden_size + 2 * cfg.hidden_size ** 2) / 1e12      # mlp2x_gelu on 576 tokens
     q, h, H = 576, 1024, cfg.hidden_size
+    kv_tok = sum(cfg.mm_vision_tower_aux_token_len_list)      # the K / V projections run over every grid token
 
     def layer(D):
-        return q * 2 * (h * h + (D + h) * h + h * h + 2 * T * h * h + h * h + h * h + h * D)
+        return 2 * (q * (h * h + (D + h) * h + h * h + h * h + h * h + h * D) + 2 * kv_tok * h * h)
     conn = cfg.connector_depth * layer(h)
     inllm = (0 if cfg.connector_only else cfg.num_of_vision_sampler_layers) * layer(H)
-    aux = 0.012e12 * T / 4
+    aux = (0.012e12 * T / 4) if aux_tf is None else aux_tf * 1e12
     proj = q * 2 * (h * H + H * H)
     return (conn + inllm + aux + proj) / 1e12
 
@@ -367,6 +382,8 @@ def ncu_traffic(key):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    if CONFIGS[args.config]["baseline_config"] is None:
+        raise SystemExit(f"--impl reference is defined for the BASELINE.json configs (8b-ddp, 7b-clip-mlp, 13b-zero2), not {args.config}")
     from oracle import cpu_arm
     c = CONFIGS[args.config]
     steps, warm = max(1, args.steps), max(1, args.warmup)
@@ -394,7 +411,8 @@ def main():
     ap.add_argument("--config", default=os.environ.get("CB_BENCH_CONFIG", "8b-ddp"), choices=sorted(CONFIGS))
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("CB_MICRO_BATCH", "0")))
     ap.add_argument("--seq", type=int, default=0)
-    ap.add_argument("--recompute", type=int, default=int(os.environ.get("CB_RECOMPUTE", "0")))
+    ap.add_argument("--recompute", type=int, default=int(os.environ.get("CB_RECOMPUTE", "-1")),
+                    help="per-layer activation recompute (1 / 0); default: the config's own (0, release recipe 1)")
     ap.add_argument("--max-grad-norm", type=float, default=float(os.environ.get("CB_MAX_GRAD_NORM", "1.0")),
                     help="gradient clipping as in the reference recipe (HF Trainer default 1.0); 0 disables it")
     ap.add_argument("--bucket-mb", type=float, default=float(os.environ.get("CB_BUCKET_MB", "256")))
@@ -423,6 +441,8 @@ def main():
     lib = _lib.load()
 
     C = CONFIGS[args.config]
+    if args.recompute < 0:
+        args.recompute = C.get("recompute", 0)
     if C["zero"] == 2 and world < 2 and not args.small:
         raise SystemExit("13b-zero2 needs >= 2 GPUs (16 B/param of training state = 214 GB unsharded): launch with torchrun")
     cfg = build_config(args.config, args.small)
@@ -612,7 +632,7 @@ def main():
             roof_sva["in_step_achieved"] = by / (tms / 1000.0) / 1e9  # B=4 inputs (38 MB) are L2-resident in the step
     # executed FLOPs per sample: with the collator's label-range hint the fused loss skips the vocabulary GEMMs
     # (3 x 2*H*V per row) of rows whose shifted label is ignore_index — identical loss / gradients, fewer FLOPs
-    step_tf = C["tower_tf"] + 3 * (llm_fwd_tflop(cfg, S) + sva_fwd_tflop(cfg, len(C["towers"])))
+    step_tf = C["tower_tf"] + 3 * (llm_fwd_tflop(cfg, S) + sva_fwd_tflop(cfg, len(C["towers"]), C.get("aux_tf")))
     rows_done = sum(b - a for a, b in label_ranges) if label_ranges is not None else B * S
     skipped_tf = 3 * 2.0 * cfg.hidden_size * cfg.vocab_size * (B * S - rows_done) / B / 1e12
     model_tf = value * (step_tf - skipped_tf) if not args.small else None
@@ -640,7 +660,10 @@ def main():
                 roofline_adamw=roof_adamw,
                 model_tflops_per_gpu=(model_tf / world) if model_tf else None,
                 mfu_vs_sustained=(model_tf / world / tf_sustained) if model_tf else None)
-    if world == 1 and not args.no_cpu_baseline:
+    if C["baseline_config"] is None:
+        line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind="port",
+                                    sample="not a BASELINE.json config: the CPU arm is defined for configs 2 / 3 / 4")
+    elif world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import cpu_arm
             r = cpu_arm.run(args.config, LLMS[C["llm"]], C, steps=1, warmup=1, budget_s=30.0)

@@ -17,7 +17,7 @@ import bench  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--batch", default="1", help="batch size, or a comma-separated list (one JSON line each, one model build)")
     ap.add_argument("--prompt", type=int, default=1024)
     ap.add_argument("--new", type=int, default=64)
     ap.add_argument("--config", default="8b-ddp")
@@ -40,7 +40,12 @@ def main():
             t.load_model()
     torch.set_default_dtype(prev)
     model.eval()
-    B = args.batch
+    for B in [int(b) for b in str(args.batch).split(",")]:
+        one_batch(args, model, cfg, dev, B)
+
+
+def one_batch(args, model, cfg, dev, B):
+    from cambrian_b200 import _lib
     C = bench.CONFIGS[args.config]
     ids = torch.randint(3, cfg.vocab_size, (B, args.prompt - 599), device=dev)
     ids[:, cfg.image_position] = -200
@@ -82,7 +87,8 @@ def main():
     print(json.dumps(dict(metric="decode_ms_per_token", value=ms_tok, unit="ms", batch=B, prompt=args.prompt, new_tokens=args.new,
                           prefill_ms=t1, tokens_per_s=B * 1000.0 / ms_tok, launches_per_token=(ln - l1) / args.new,
                           decode_graph=not args.no_graph, weight_bytes=n_params * 2, floor_ms=floor, frac_of_floor=floor / ms_tok,
-                          note="floor = decoder + lm_head bf16 weights / measured HBM copy bandwidth", top_kernels=top)))
+                          note="floor = decoder + lm_head bf16 weights / measured HBM copy bandwidth", top_kernels=top)),
+          flush=True)
 
 
 if __name__ == "__main__":
