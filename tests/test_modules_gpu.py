@@ -143,7 +143,8 @@ def test_sva_sep_sampler_matches_oracle(rs, use_mask, natural):
         if "k_proj.0.bias" in k:
             # one softmax per tower with a single query: a constant added to every key cancels — the gradient is
             # structurally zero (rounding noise only) in all three arms
-            assert float(params[k].grad.float().abs().max()) <= 1e-2 * max(float(gref[2 + T].abs().max()), 1e-6) + 1e-3, k
+            scale = float(params[k.replace("0.bias", "0.weight")].grad.float().abs().max())     # the same LayerNorm's gamma
+            assert float(params[k].grad.float().abs().max()) <= 0.1 * scale + 1e-3, (k, scale)
             continue
         pc.check(params[k].grad, gr, ge, f"{tag}: grad {k}")
     pc.done()
