@@ -102,6 +102,21 @@ class ParityCollector:
         assert not self.bad, "parity failures:\n  " + "\n  ".join(self.bad)
 
 
+def assert_same_training(master, master_ref, lr, steps, what):
+    """Two runs of the same training recipe (different optimizer schedules) on the fp32 master weights.  Gradients are not
+    bit-reproducible from run to run (dQ partials are reduce-added by TMA in arrival order), and an AdamW step moves every
+    element by ~lr * sign(g): an element whose gradient sits at the rounding-noise level can land one step apart.  So: no
+    element further apart than the 2 * lr * steps an optimizer can move it, and the tensors equal in the Frobenius sense —
+    a schedule bug (a bucket updated twice, not at all, or from stale gradients) moves whole buckets by ~lr per element,
+    i.e. >= 5e-2 relative on the 0.02-rms weights."""
+    d = (master.float() - master_ref.float()).abs()
+    fro = (d.double().norm() / master_ref.double().norm()).item()
+    _report(dict(what=f"{what}: fp32 master", max_abs=d.max().item(), fro=fro,
+                 frac_gt_0p1lr=(d > 0.1 * lr).float().mean().item(), bound_abs=2 * lr * steps))
+    assert d.max().item() <= 2.05 * lr * steps, (what, d.max().item())
+    assert fro < 1e-2, (what, fro)
+
+
 def oracle_device():
     """Device the (torch) oracle runs on in `-m gpu` tests: the GPU, so full-size fp32 / eager-bf16 oracles take
     seconds.  TF32 is disabled so 'fp32' means fp32."""
