@@ -109,10 +109,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     N, Kb = (bc, br) if b_mn else (br, bc)
     if K != Kb or ba != bb:
         raise ValueError(f"gemm: shape mismatch a={tuple(a.shape)} b={tuple(b.shape)} a_mn={a_mn} b_mn={b_mn}")
-    if (_GEMV and M <= 8 and not batched and not a_mn and not b_mn and act in (None, "none") and colscale is None
+    # decode step: weight streaming.  The CUDA-core GEMV is FMA-bound at 6-8 rows (2.0-2.6 TB/s at M = 8): for wide outputs
+    # the 128-row tcgen05 tile streams the weights faster there (measured, profiles/r02_probe_gemv.log: N = 28672: 61 vs
+    # 97 us, N = 128256: 257 vs 396 us at M = 8; N <= 6144: GEMV wins at every M), so those keep the tensor-core kernel.
+    if (_GEMV and M <= 8 and not (M >= 6 and N >= 16384) and not batched and not a_mn and not b_mn
+            and act in (None, "none") and colscale is None
             and not accumulate and alpha == 1.0 and force_bn == 0 and K % 8 == 0 and lda % 8 == 0 and ldb % 8 == 0
             and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
-        return gemv(a, b, bias=bias, residual=residual, out=out, out_dtype=out_dtype)      # decode step: weight streaming
+        return gemv(a, b, bias=bias, residual=residual, out=out, out_dtype=out_dtype)
     if out is None:
         if accumulate:
             raise ValueError("gemm: accumulate=True needs an explicit `out`")
