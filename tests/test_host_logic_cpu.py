@@ -121,6 +121,38 @@ def test_sep_sampler_state_dict_follows_the_reference_layout():
           torch.zeros(4, 9, 1024))
 
 
+def test_decode_projection_dispatch(monkeypatch):
+    """ops.gemm routes decode-shaped projections (M <= 8 rows, plain epilogue) to the weight-streaming GEMV, except 6-8
+    rows on wide outputs where the tcgen05 tile measured faster (profiles/r02_probe_gemv.log); training shapes, transposed
+    operands and fused epilogues always take the tensor-core kernel.  Host-side routing only: both kernels are faked."""
+    from cambrian_b200 import _lib, ops
+    calls = []
+
+    class FakeLib:
+        def cb_gemm_bf16(self, *a):
+            calls.append("gemm")
+            return 0
+
+    monkeypatch.setattr(ops, "_require_cuda_bf16", lambda *a: None)
+    monkeypatch.setattr(ops, "gemv", lambda a, b, **kw: calls.append("gemv") or torch.empty(a.shape[0], b.shape[0]))
+    monkeypatch.setattr(_lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(ops, "stream", lambda: 0)
+
+    def route(M, N, K=64, **kw):
+        calls.clear()
+        ops.gemm(torch.zeros(M, K, dtype=torch.bfloat16), torch.zeros(N, K, dtype=torch.bfloat16), **kw)
+        return calls[-1]
+
+    assert route(1, 128256) == "gemv" and route(4, 28672) == "gemv" and route(5, 28672) == "gemv"
+    assert route(8, 4096) == "gemv" and route(8, 6144) == "gemv"
+    assert route(8, 28672) == "gemm" and route(6, 16384) == "gemm" and route(8, 128256) == "gemm"
+    assert route(9, 4096) == "gemm" and route(2048, 4096) == "gemm"
+    assert route(1, 4096, act="gelu") == "gemm"
+    calls.clear()
+    ops.gemm(torch.zeros(64, 8, dtype=torch.bfloat16), torch.zeros(64, 32, dtype=torch.bfloat16), a_mn=True, b_mn=True)
+    assert calls == ["gemm"]
+
+
 # ------------------------------------------------------------------------------------------------ model plumbing
 def test_state_dict_keys_follow_the_reference_layout():
     from cambrian_b200.model.language_model.cambrian_llama import CambrianLlamaForCausalLM
