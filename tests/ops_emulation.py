@@ -191,6 +191,29 @@ def add_(dst, src):
     return dst
 
 
+def adamw(p32, m, v, g16, p16, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, clip_coef=None, background=False):
+    """adamw_kernel (elementwise.cu): torch.optim.AdamW arithmetic on fp32 master / moments, bf16 gradients in, bf16 copy out."""
+    gs = float(clip_coef[0]) if clip_coef is not None else grad_scale
+    g = g16.float() * gs
+    bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+    p32.mul_(1.0 - lr * wd)
+    m.mul_(beta1).add_(g, alpha=1.0 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+    p32.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
+    p16.copy_(p32.to(torch.bfloat16))
+
+
+def sumsq_accumulate(g16, acc, ws, background=True):
+    acc[0] += g16.float().pow(2).sum()
+
+
+def clip_coef(sumsq, max_norm, inv_world, coef):
+    norm = sumsq[0].sqrt() * inv_world
+    coef[0] = inv_world * min(1.0, max_norm / (float(norm) + 1e-6))
+    coef[1] = norm
+    sumsq[0] = 0.0
+
+
 def require_cuda_bf16_params(params, what):
     if any(p.dtype != torch.bfloat16 for p in params):
         raise RuntimeError(f"cambrian_b200 {what} run in bf16")
@@ -198,12 +221,21 @@ def require_cuda_bf16_params(params, what):
 
 _NAMES = ("gemm", "linear", "f32_to_bf16", "layernorm_fwd", "layernorm_bwd", "sva_window_attn_fwd", "sva_window_attn_bwd",
           "act_fwd", "act_bwd", "tower_combine_fwd", "tower_combine_bwd", "pos_grad", "bilinear", "bilinear_bwd",
-          "group_colsum", "group_broadcast", "add_", "require_cuda_bf16_params")
+          "group_colsum", "group_broadcast", "add_", "require_cuda_bf16_params", "adamw", "sumsq_accumulate", "clip_coef")
 
 
-def install(monkeypatch):
+class _Setter:
+    """monkeypatch look-alike for spawned worker processes (the process ends with the test)."""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+
+def install(monkeypatch=None):
     """Replace the emulated entry points of `cambrian_b200.ops` for the duration of one test (pytest's monkeypatch undoes
-    it); every other op keeps raising without the CUDA library."""
+    it; a spawned worker passes nothing); every other op keeps raising without the CUDA library."""
+    monkeypatch = monkeypatch or _Setter
     from cambrian_b200 import ops
     for n in _NAMES:
         monkeypatch.setattr(ops, n, globals()[n])
