@@ -214,6 +214,199 @@ def clip_coef(sumsq, max_norm, inv_world, coef):
     sumsq[0] = 0.0
 
 
+# ---- decoder layer, splice, loss (norm.cu, attention.cu, elementwise.cu) ---------------------------------------------
+def rmsnorm_fwd(x, gamma, eps=1e-6, hf_cast=False, save_stats=False):
+    """y = gamma * x_hat, x_hat = x * rsqrt(mean(x^2) + eps); hf_cast rounds x_hat to bf16 first (HF LlamaRMSNorm), else
+    the product is rounded once (the reference's training-time patch, train_fsdp.py:1429-1435)."""
+    C = x.shape[-1]
+    xf = x.reshape(-1, C).float()
+    rstd = torch.rsqrt(xf.pow(2).mean(-1) + eps)
+    xh = xf * rstd[:, None]
+    if hf_cast:
+        xh = xh.to(torch.bfloat16).float()
+    y = (gamma.float() * xh).to(torch.bfloat16).view(x.shape)
+    return (y, rstd) if save_stats else y
+
+
+def rmsnorm_bwd(dy, x, gamma, rstd, dres=None):
+    C = x.shape[-1]
+    xf, dyf = x.reshape(-1, C).float(), dy.reshape(-1, C).float()
+    xh = xf * rstd[:, None]
+    g = dyf * gamma.float()
+    dx = rstd[:, None] * (g - xh * (g * xh).mean(-1, keepdim=True))
+    if dres is not None:
+        dx = dx + dres.reshape(-1, C).float()
+    return dx.to(torch.bfloat16).view(x.shape), (dyf * xh).sum(0).to(torch.bfloat16)
+
+
+def rope_(buf, pos, cos_t, sin_t, n_heads, hd, inverse=False):
+    """In place on the first n_heads * hd columns of the packed [rows, ld] buffer, rotate_half convention; cos / sin
+    [max_pos, hd/2] fp32 rounded to bf16 like HF; inverse = the transposed rotation (backward)."""
+    rows, half = buf.shape[0], hd // 2
+    p = pos.clamp(0, cos_t.shape[0] - 1)
+    c = cos_t[p].to(torch.bfloat16).float()[:, None, :]
+    s_ = sin_t[p].to(torch.bfloat16).float()[:, None, :]
+    if inverse:
+        s_ = -s_
+    x = buf[:, : n_heads * hd].float().reshape(rows, n_heads, hd)
+    x1, x2 = x[..., :half], x[..., half:]
+    rb = lambda t: t.to(torch.bfloat16).float()          # every product is rounded to bf16, as in the kernel / HF
+    o = torch.cat([rb(x1 * c) + rb(-x2 * s_), rb(x2 * c) + rb(x1 * s_)], -1)
+    buf[:, : n_heads * hd] = o.reshape(rows, n_heads * hd).to(torch.bfloat16)
+    return buf
+
+
+def _attn(q, k, v, causal, kmask, scale):
+    B, Sq, nh, hd = q.shape
+    Skv, nkv = k.shape[1], k.shape[2]
+    Q = q.transpose(1, 2)
+    K = k.transpose(1, 2).repeat_interleave(nh // nkv, 1)
+    V = v.transpose(1, 2).repeat_interleave(nh // nkv, 1)
+    s = Q @ K.transpose(-1, -2) * (scale if scale is not None else hd ** -0.5)
+    allow = torch.ones(Sq, Skv, dtype=torch.bool)
+    if causal:
+        allow = allow.tril(Skv - Sq)
+    allow = allow[None, None]
+    if kmask is not None:
+        allow = allow & kmask.bool()[:, None, None, :]
+    p = torch.nan_to_num(torch.softmax(s.masked_fill(~allow, float("-inf")), -1), 0.0)
+    return (p @ V).transpose(1, 2)
+
+
+def attn_fwd(q, k, v, *, causal, kmask=None, scale=None, need_lse=False, out=None):
+    o = _attn(q.float(), k.float(), v.float(), causal, kmask, scale).to(torch.bfloat16).contiguous()
+    if out is not None:
+        out.copy_(o)
+        o = out
+    return (o, torch.zeros(q.shape[0], q.shape[2], q.shape[1])) if need_lse else o
+
+
+def attn_bwd(q, k, v, o, do, lse, *, causal, kmask=None, scale=None, dq=None, dk=None, dv=None):
+    qf, kf, vf = (t.float().detach().requires_grad_() for t in (q, k, v))
+    with torch.enable_grad():
+        out = _attn(qf, kf, vf, causal, kmask, scale)
+    gq, gk, gv = torch.autograd.grad(out, [qf, kf, vf], do.float())
+    res = []
+    for g, dst in ((gq, dq), (gk, dk), (gv, dv)):
+        g = g.to(torch.bfloat16)
+        if dst is not None:
+            dst.copy_(g)
+            g = dst
+        res.append(g)
+    return tuple(res)
+
+
+def swiglu_fwd(gate, up):
+    return (F.silu(gate.float()).to(torch.bfloat16).float() * up.float()).to(torch.bfloat16)
+
+
+def swiglu_bwd(dout, gate, up, dgate, dup):
+    g, u, d = gate.float(), up.float(), dout.float()
+    sg = torch.sigmoid(g)
+    dup.copy_((d * g * sg).to(torch.bfloat16))
+    dgate.copy_((d * u * sg * (1 + g * (1 - sg))).to(torch.bfloat16))
+
+
+def mlp_gate_up(h2d, w_gu):
+    gu = gemm(h2d, w_gu)
+    I = w_gu.shape[0] // 2
+    return gu, swiglu_fwd(gu[:, :I], gu[:, I:])
+
+
+def _span_index(B, S, start, q_side, per_sample_start=None):
+    """flat positions (b * S + s) of the q x q latent rows of the image span (q rows of q latents + 1 newline)."""
+    rows = torch.arange(q_side)[:, None] * (q_side + 1) + torch.arange(q_side)[None, :]
+    return (torch.arange(B)[:, None] * S + start + rows.reshape(1, -1)).reshape(-1)
+
+
+def span_gather(hidden, start, q_side):
+    B, S, H = hidden.shape
+    return hidden.reshape(B * S, H)[_span_index(B, S, start, q_side)].clone()
+
+
+def span_scatter_(hidden, lat, start, q_side):
+    B, S, H = hidden.shape
+    hidden.view(B * S, H)[_span_index(B, S, start, q_side)] = lat.to(hidden.dtype)
+    return hidden
+
+
+def _splice_maps(ids, img_start, q_side, has_img):
+    """per flattened position: kind 0 = text, 1 = image latent, 2 = newline; and the image row / newline row it maps to."""
+    B, S = ids.shape
+    span = q_side * (q_side + 1)
+    pos = torch.arange(S)[None].expand(B, S)
+    st = img_start.to(torch.long)[:, None] if (has_img and img_start is not None) else torch.full((B, 1), -1)
+    inside = (st >= 0) & (pos >= st) & (pos < st + span)
+    k = (pos - st).clamp(min=0)
+    row, col = k // (q_side + 1), k % (q_side + 1)
+    kind = torch.where(inside, torch.where(col == q_side, 2, 1), 0)
+    img_row = torch.arange(B)[:, None] * q_side * q_side + row * q_side + col.clamp(max=q_side - 1)
+    nl_row = torch.arange(B)[:, None] * q_side + row
+    return kind.reshape(-1), img_row.reshape(-1), nl_row.reshape(-1)
+
+
+def embed_splice(ids, img_start, embed, img, newline, q_side):
+    B, S = ids.shape
+    H = embed.shape[1]
+    idc = ids.reshape(-1).clone()
+    idc[(idc < 0) | (idc >= embed.shape[0])] = 0
+    out = embed[idc].clone()
+    if img is not None:
+        kind, img_row, _ = _splice_maps(ids, img_start, q_side, True)
+        out[kind == 1] = img.reshape(-1, H)[img_row[kind == 1]]
+        out[kind == 2] = newline
+    return out.view(B, S, H)
+
+
+def embed_splice_bwd(dout, ids, img_start, d_embed, q_side, has_img):
+    B, S, H = dout.shape
+    if not has_img:
+        return None, None
+    kind, img_row, nl_row = _splice_maps(ids, img_start, q_side, True)
+    d = dout.reshape(-1, H)
+    d_img = torch.zeros(B * q_side * q_side, H, dtype=torch.bfloat16)
+    d_nl = torch.zeros(B * q_side, H, dtype=torch.bfloat16)
+    d_img[img_row[kind == 1]] = d[kind == 1]
+    d_nl[nl_row[kind == 2]] = d[kind == 2]
+    return d_img.view(B, q_side * q_side, H), d_nl
+
+
+def embed_grad_sorted(dout, ids, img_start, d_embed, q_side):
+    B, S, H = dout.shape
+    idc = ids.reshape(-1).clone()
+    idc[(idc < 0) | (idc >= d_embed.shape[0])] = 0
+    kind, _, _ = _splice_maps(ids, img_start, q_side, img_start is not None)
+    text = kind == 0
+    acc = torch.zeros(d_embed.shape, dtype=torch.float32)
+    acc.index_add_(0, idc[text], dout.reshape(-1, H)[text].float())
+    touched = torch.zeros(d_embed.shape[0], dtype=torch.bool)
+    touched[idc[text]] = True
+    d_embed[touched] = (d_embed[touched].float() + acc[touched]).to(d_embed.dtype)
+
+
+def cross_entropy(logits, labels, loss_rows, loss_acc, grad_scale, write_grad, ignore_index=-100, scale_dev=None):
+    """loss_row = logsumexp(fp32 logits) - logit[label] (0 for ignored rows); loss_acc[0] += sum, [1] += count; with
+    write_grad the rows are overwritten IN PLACE by (softmax - onehot) * grad_scale (* scale_dev[0])."""
+    rows, V = logits.shape
+    if scale_dev is not None:
+        grad_scale = grad_scale * float(scale_dev[0])
+    lf = logits.float()
+    valid = (labels != ignore_index) & (labels >= 0) & (labels < V)
+    lab = labels.clamp(0, V - 1)
+    lse = torch.logsumexp(lf, -1)
+    lr = torch.where(valid, lse - lf.gather(1, lab[:, None])[:, 0], torch.zeros_like(lse))
+    loss_rows.copy_(lr)
+    if loss_acc is not None:
+        loss_acc[0] += lr.sum()
+        loss_acc[1] += valid.sum()
+    if write_grad:
+        g = torch.softmax(lf, -1)
+        g[torch.arange(rows), lab] -= 1.0
+        g = g * grad_scale
+        g[~valid] = 0.0
+        logits.copy_(g.to(logits.dtype))
+
+
 def require_cuda_bf16_params(params, what):
     if any(p.dtype != torch.bfloat16 for p in params):
         raise RuntimeError(f"cambrian_b200 {what} run in bf16")
@@ -221,7 +414,9 @@ def require_cuda_bf16_params(params, what):
 
 _NAMES = ("gemm", "linear", "f32_to_bf16", "layernorm_fwd", "layernorm_bwd", "sva_window_attn_fwd", "sva_window_attn_bwd",
           "act_fwd", "act_bwd", "tower_combine_fwd", "tower_combine_bwd", "pos_grad", "bilinear", "bilinear_bwd",
-          "group_colsum", "group_broadcast", "add_", "require_cuda_bf16_params", "adamw", "sumsq_accumulate", "clip_coef")
+          "group_colsum", "group_broadcast", "add_", "require_cuda_bf16_params", "adamw", "sumsq_accumulate", "clip_coef", "rmsnorm_fwd", "rmsnorm_bwd",
+          "rope_", "attn_fwd", "attn_bwd", "swiglu_fwd", "swiglu_bwd", "mlp_gate_up", "span_gather", "span_scatter_",
+          "embed_splice", "embed_splice_bwd", "embed_grad_sorted", "cross_entropy")
 
 
 class _Setter:

@@ -116,6 +116,7 @@ def _engine_worker(rank, world, port, q, zero, clip):
     write into the flat gradient buffer and notify the engine), three steps on rank- and step-dependent data."""
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // (2 * world)))   # two workers share the host: no oversubscription
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         ops_emulation.install()

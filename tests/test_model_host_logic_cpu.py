@@ -1,0 +1,214 @@
+"""CPU coverage of the HOST logic of the whole trainable path (cambrian_arch -> cambrian_llama -> autograd blocks ->
+TrainEngine): `CambrianLlamaForCausalLM.forward` / backward and the engine's step run on the CPU with the kernels replaced
+by the plain-torch stand-ins of tests/ops_emulation.py (test infrastructure, monkeypatched per test) and the frozen towers
+replaced by seeded feature tensors (the towers are forward-only and covered at full depth under `-m gpu`).  What is
+exercised is the product's Python: image-span location / expansion, projector and SVA wiring, splice, the decoder loop
+with its in-LLM SVA sites, fused and unfused loss, every block's hand-written backward, gradient routing into the
+engine's flat buffers, bucket collectives launched from inside backward on two gloo ranks.  Checked against the oracle.
+Kernel numerics are NOT covered here — `-m gpu` does that."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ops_emulation  # noqa: E402
+from helpers import oracle_cfg, tiny_cambrian_config  # noqa: E402
+from oracle import cambrian_oracle as O  # noqa: E402
+
+
+def _fro(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-30)).item()
+
+
+def _build(cfg, seed=3):
+    from cambrian_b200.model.language_model.cambrian_llama import CambrianLlamaForCausalLM
+    torch.manual_seed(seed)
+    cfg.dino_config_overrides = dict(hidden_size=384, num_hidden_layers=2, num_attention_heads=6, mlp_ratio=4)
+    model = CambrianLlamaForCausalLM(cfg)
+    for t in model.get_model().vision_tower_aux_list:
+        t.load_model()
+    with torch.no_grad():
+        for n_, p in model.named_parameters():
+            if "pos_embed" in n_:
+                p.mul_(0.1)
+    return model.to(torch.bfloat16)
+
+
+def _batch(cfg, B=2, S=64, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    q = int(cfg.image_token_len ** 0.5)
+    span = q * (q + 1)
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=g)
+    p0 = cfg.image_position
+    ids[:, p0] = -200
+    ids[:, p0 + 1:p0 + span] = 0
+    labels = ids.clone()
+    labels[:, :p0 + span] = -100
+    attn = torch.ones(B, S, dtype=torch.bool)
+    attn[1, S - 6:] = False
+    labels[1, S - 6:] = -100
+    pos = (attn.long().cumsum(1) - 1).clamp(min=0)
+    masks = []
+    for L in cfg.mm_vision_tower_aux_token_len_list:
+        r = int(L ** 0.5) // q
+        mk = torch.rand(B * q * q, r * r, generator=g) > 0.2
+        mk[mk.sum(1) == 0] = True
+        masks.append(mk)
+    return ids, labels, attn, pos, masks
+
+
+def _tower_feats(model, cfg, B, seed):
+    """Stand-in for the frozen towers' outputs: [B, N_i, C_i] bf16 with the token counts / widths the towers declare."""
+    g = torch.Generator().manual_seed(seed)
+    towers = model.get_model().vision_tower_aux_list
+    return [torch.randn(B, t.num_patches, t.hidden_size, generator=g).bfloat16() for t in towers]
+
+
+def _oracle(model, cfg, ids, labels, attn, pos, feats, masks):
+    sd = {k: v.detach().float().clone().requires_grad_() for k, v in model.state_dict().items()}
+    ocfg = oracle_cfg(cfg)
+    if cfg.mm_projector_type == "sva":
+        img, feats_w, ctx_q = O.connector(sd, ocfg, [f.float() for f in feats], masks)
+    else:
+        img, feats_w, ctx_q = O.mlp2x_gelu(sd, "model.mm_projector.", torch.cat([f.float() for f in feats], -1)), None, None
+        B, q = img.shape[0], int(cfg.image_token_len ** 0.5)
+        nl = sd["model.image_newline"][None, None, None, :].expand(B, q, 1, -1)
+        img = torch.cat([img.view(B, q, q, -1), nl], 2).flatten(1, 2)
+    hid = O.decoder(sd, ocfg, O.splice(sd, ids, img), pos, attn, feats_w, masks, ctx_q)
+    logits, loss = O.lm_loss(sd, hid, labels)
+    return logits, loss, sd
+
+
+@pytest.mark.parametrize("fused,sva", [(False, True), (True, True), (True, False)])
+def test_full_trainable_path_host_logic(monkeypatch, fused, sva):
+    ops_emulation.install(monkeypatch)
+    cfg = tiny_cambrian_config(sva=sva, connector_only=not sva)
+    if not sva:
+        cfg.mm_vision_tower_aux_list = cfg.mm_vision_tower_aux_list[1:2]         # config 2: one CLIP tower + mlp2x_gelu
+        cfg.mm_vision_tower_aux_token_len_list = [cfg.image_token_len]
+    cfg.fused_lm_loss = fused
+    model = _build(cfg)
+    model.train()
+    ids, labels, attn, pos, masks = _batch(cfg)
+    if not sva:
+        masks = None
+    feats = _tower_feats(model, cfg, ids.shape[0], 11)
+    monkeypatch.setattr(type(model), "encode_images", lambda self, imgs: feats)
+    images = [torch.zeros(ids.shape[0], 3, 8, 8, dtype=torch.bfloat16) for _ in feats]   # only their batch size is read
+    out = model(input_ids=ids, labels=labels, attention_mask=attn, position_ids=pos, images=images,
+                image_aux_attention_masks_list=masks)
+    out.loss.backward()
+    ref_logits, ref_loss, sd = _oracle(model, cfg, ids, labels, attn, pos, feats, masks)
+    ref_loss.backward()
+    assert abs(out.loss.item() - ref_loss.item()) <= 2e-2 * abs(ref_loss.item()), (out.loss.item(), ref_loss.item())
+    if not fused:
+        assert _fro(out.logits[attn], ref_logits[attn]) < 3e-2
+    worst = ("", 0.0)
+    checked = 0
+    for k, p in model.named_parameters():
+        g = sd[k].grad
+        if g is None or float(g.abs().max()) == 0.0:
+            assert p.grad is None or float(p.grad.float().abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, f"missing grad for {k}"
+        e = _fro(p.grad, g)
+        checked += 1
+        if e > worst[1]:
+            worst = (k, e)
+    assert checked > 30 and worst[1] < 5e-2, worst
+
+
+def test_decoder_layer_recompute_gives_the_same_gradients(monkeypatch):
+    """Per-layer activation recompute (gradient_checkpointing) re-runs the block's forward inside backward: identical
+    gradients to the stored-activation path (same stand-in kernels, so bit-identical here)."""
+    ops_emulation.install(monkeypatch)
+    grads = []
+    for ckpt in (False, True):
+        cfg = tiny_cambrian_config()
+        cfg.fused_lm_loss = True
+        model = _build(cfg)
+        model.train()
+        model.get_model().gradient_checkpointing = ckpt
+        ids, labels, attn, pos, masks = _batch(cfg)
+        feats = _tower_feats(model, cfg, ids.shape[0], 11)
+        monkeypatch.setattr(type(model), "encode_images", lambda self, imgs: feats)
+        images = [torch.zeros(ids.shape[0], 3, 8, 8, dtype=torch.bfloat16) for _ in feats]
+        model(input_ids=ids, labels=labels, attention_mask=attn, position_ids=pos, images=images,
+              image_aux_attention_masks_list=masks).loss.backward()
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    assert grads[0].keys() == grads[1].keys()
+    assert all(torch.equal(grads[0][k], grads[1][k]) for k in grads[0])
+
+
+# ------------------------------------------------------------------------------------------------ N > 1 on gloo
+def _train_worker(rank, world, port, q, zero):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // (2 * world)))   # two workers share the host: no oversubscription
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ops_emulation.install()
+        from cambrian_b200.engine import TrainEngine
+        cfg = tiny_cambrian_config()
+        cfg.fused_lm_loss = True
+        model = _build(cfg)                                    # same seed on every rank: identical replicas
+        model.train()
+        ids, labels, attn, pos, masks = _batch(cfg, seed=7 + rank)          # every rank its own data, fixed over the steps
+        feats = _tower_feats(model, cfg, ids.shape[0], 100 + rank)
+        type(model).encode_images = lambda self, imgs: feats
+        images = [torch.zeros(ids.shape[0], 3, 8, 8, dtype=torch.bfloat16) for _ in feats]
+        calls = {"n": 0, "bwd": False}
+        ar0 = dist.all_reduce
+
+        def counting(*a, **k):
+            calls["n"] += int(calls["bwd"])
+            return ar0(*a, **k)
+        dist.all_reduce = counting
+        eng = TrainEngine(model, lr=2e-3, bucket_mb=1.0, zero_stage=zero, max_grad_norm=1.0)
+        losses = []
+        for _ in range(3):
+            eng.zero_grad()
+            loss = model(input_ids=ids, labels=labels, attention_mask=attn, position_ids=pos, images=images,
+                         image_aux_attention_masks_list=masks).loss
+            calls["bwd"] = True
+            loss.backward()
+            calls["bwd"] = False
+            eng.step()
+            losses.append(float(loss.detach()))
+        t = eng.flat_p.float().clone()
+        lo, hi = t.clone(), t.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok = bool(torch.equal(lo, hi))                                      # replicas bit-identical after 3 steps
+        ok &= eng._overlap_ok and len(eng.buckets) >= 4
+        ok &= calls["n"] >= len(eng.buckets)                               # collectives were issued from inside backward
+        ok &= losses[-1] < losses[0]                                        # and the job trains
+        if zero == 2:
+            ok &= eng.master.numel() * world == eng.total
+        q.put((rank, bool(ok), f"losses {losses} buckets {len(eng.buckets)} in-backward collectives {calls['n']} "
+                                f"overlap_ok {eng._overlap_ok}"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, False, traceback.format_exc()[-2500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("zero", [0, 2])
+def test_whole_model_data_parallel_two_ranks_gloo(zero):
+    """SURVEY §8e on CPU: the full tiny Cambrian model (connector + decoder with in-LLM SVA sites + fused loss) under
+    TrainEngine on two gloo ranks — DDP all-reduce buckets and the ZeRO-2 sharded optimizer, gradient clipping on."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() + 29 * zero) % 2000
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, zero)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+    assert all(r[1] for r in res), [r[2] for r in res]
