@@ -407,6 +407,48 @@ def cross_entropy(logits, labels, loss_rows, loss_acc, grad_scale, write_grad, i
         logits.copy_(g.to(logits.dtype))
 
 
+# ---- dynamic-shape (inference) branch ------------------------------------------------------------------------------------
+def _span_index_hw(B, S, start, q_h, q_w):
+    rows = torch.arange(q_h)[:, None] * (q_w + 1) + torch.arange(q_w)[None, :]
+    return (torch.arange(B)[:, None] * S + start + rows.reshape(1, -1)).reshape(-1)
+
+
+def span_gather_hw(hidden, start, q_h, q_w):
+    B, S, H = hidden.shape
+    return hidden.reshape(B * S, H)[_span_index_hw(B, S, start, q_h, q_w)].clone()
+
+
+def span_scatter_hw_(hidden, lat, start, q_h, q_w):
+    B, S, H = hidden.shape
+    hidden.view(B * S, H)[_span_index_hw(B, S, start, q_h, q_w)] = lat.reshape(-1, H).to(hidden.dtype)
+    return hidden
+
+
+def window_gather(feat, q_side, crop=None):
+    B, N, C = feat.shape
+    side = int(round(N ** 0.5))
+    if side * side != N or side % q_side != 0:
+        raise AssertionError("window_gather: token grid is not a square multiple of the query grid")
+    r = side // q_side
+    y0, y1, x0, x1 = crop if crop is not None else (0, q_side, 0, q_side)
+    t = feat.reshape(B, q_side, r, q_side, r, C).permute(0, 1, 3, 2, 4, 5)[:, y0:y1, x0:x1]
+    return t.reshape(B * (y1 - y0) * (x1 - x0), r * r, C).contiguous()
+
+
+def embed_splice_ragged(embed_w, img, newline, src, batch, max_len):
+    H = embed_w.shape[1]
+    src = src.to(torch.long)
+    out = torch.zeros(batch * max_len, H, dtype=torch.bfloat16)
+    tok = src >= 0
+    out[tok] = embed_w[src[tok]]
+    nl = src == -(2 ** 31)
+    out[nl] = newline
+    im = (src <= -2) & ~nl
+    if im.any():
+        out[im] = img.reshape(-1, H)[-2 - src[im]]
+    return out.view(batch, max_len, H)
+
+
 def require_cuda_bf16_params(params, what):
     if any(p.dtype != torch.bfloat16 for p in params):
         raise RuntimeError(f"cambrian_b200 {what} run in bf16")
@@ -416,7 +458,8 @@ _NAMES = ("gemm", "linear", "f32_to_bf16", "layernorm_fwd", "layernorm_bwd", "sv
           "act_fwd", "act_bwd", "tower_combine_fwd", "tower_combine_bwd", "pos_grad", "bilinear", "bilinear_bwd",
           "group_colsum", "group_broadcast", "add_", "require_cuda_bf16_params", "adamw", "sumsq_accumulate", "clip_coef", "rmsnorm_fwd", "rmsnorm_bwd",
           "rope_", "attn_fwd", "attn_bwd", "swiglu_fwd", "swiglu_bwd", "mlp_gate_up", "span_gather", "span_scatter_",
-          "embed_splice", "embed_splice_bwd", "embed_grad_sorted", "cross_entropy")
+          "embed_splice", "embed_splice_bwd", "embed_grad_sorted", "cross_entropy", "span_gather_hw", "span_scatter_hw_",
+          "window_gather", "embed_splice_ragged")
 
 
 class _Setter:

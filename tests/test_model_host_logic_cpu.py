@@ -143,6 +143,65 @@ def test_decoder_layer_recompute_gives_the_same_gradients(monkeypatch):
     assert all(torch.equal(grads[0][k], grads[1][k]) for k in grads[0])
 
 
+def test_dynamic_shape_branch_host_logic(monkeypatch):
+    """The reference's per-sample (non-XLA) branch for non-square images (cambrian_arch.py:289-330, :422-451, :493-609;
+    cambrian_llama.py:208-253): unpadded query grids, ragged splice, ragged in-LLM SVA sites — logits vs the oracle."""
+    ops_emulation.install(monkeypatch)
+    cfg = tiny_cambrian_config()
+    model = _build(cfg).eval()
+    g = torch.Generator().manual_seed(17)
+    B, L = 2, 40
+    ids = torch.randint(3, cfg.vocab_size, (B, L), generator=g)
+    ids[:, cfg.image_position] = -200                        # bare <image> indicator: the branch expands it per sample
+    attn = torch.ones(B, L, dtype=torch.bool)
+    attn[1, L - 7:] = False
+    feats = _tower_feats(model, cfg, B, 23)
+    monkeypatch.setattr(type(model), "encode_images", lambda self, imgs: feats)
+    images = [torch.zeros(B, 3, 8, 8, dtype=torch.bfloat16) for _ in feats]
+    sizes = [(800, 400), (200, 500)]                         # 4x4 query grid -> (2, 4) and (4, 2) after unpadding
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=attn, images=images, image_sizes=sizes)
+        sd = {k: v.detach().float() for k, v in model.state_dict().items()}
+        ocfg = oracle_cfg(cfg)
+        emb, _, am, pos, ff, mf, fs, ctx = O.prepare_dynamic(sd, ocfg, [f.float() for f in feats], ids, attn, None, sizes)
+        assert fs == [(2, 4), (4, 2)]
+        ref_logits, _ = O.lm_loss(sd, O.decoder_dynamic(sd, ocfg, emb, pos, am, ff, mf, ctx, fs), None)
+    assert out.logits.shape == ref_logits.shape
+    assert _fro(out.logits[am], ref_logits[am]) < 3e-2
+
+
+def test_greedy_generate_host_logic(monkeypatch):
+    """generate(): multimodal prefill + KV-cache decode loop (the eager per-token loop; the CUDA-graph replay needs a GPU),
+    token-exact against the oracle's greedy decode on the peaked test model of tests/test_parity_gpu.py."""
+    from test_parity_gpu import _oracle_greedy
+    ops_emulation.install(monkeypatch)
+    cfg = tiny_cambrian_config()
+    cfg.fused_lm_loss = True
+    model = _build(cfg)
+    with torch.no_grad():
+        emb = model.get_model().embed_tokens.weight
+        perm = torch.randperm(emb.shape[0], generator=torch.Generator().manual_seed(9))
+        model.lm_head.weight.copy_(emb[perm] * 24.0)
+        for n_, p in model.named_parameters():
+            if ((n_.endswith("o_proj.weight") and "layers." in n_ and "vision_sampler" not in n_)
+                    or n_.endswith("down_proj.weight")
+                    or ("vision_sampler_layers" in n_ and n_.endswith("proj_out.linear_2.weight"))):
+                p.mul_(0.4)
+    model.eval()
+    ids, labels, attn, pos, masks = _batch(cfg, S=96)
+    S0, n_new = 40, 12
+    gen_ids = ids[:1, :S0].clone()
+    feats = [f[:1] for f in _tower_feats(model, cfg, 2, 31)]
+    monkeypatch.setattr(type(model), "encode_images", lambda self, imgs: feats)
+    images = [torch.zeros(1, 3, 8, 8, dtype=torch.bfloat16) for _ in feats]
+    new = model.generate(gen_ids, images=images, image_sizes=[(56, 56)], max_new_tokens=n_new, do_sample=False)
+    sd = {k: v.detach().float() for k, v in model.state_dict().items()}
+    want, margins = _oracle_greedy(sd, cfg, oracle_cfg(cfg), [f.float() for f in feats], gen_ids, n_new, torch.float32,
+                                   torch.device("cpu"))
+    assert new[0].tolist() == want, (new[0].tolist(), want, margins)
+    assert len(set(want)) >= 4
+
+
 # ------------------------------------------------------------------------------------------------ N > 1 on gloo
 def _train_worker(rank, world, port, q, zero):
     import torch.distributed as dist
