@@ -256,6 +256,53 @@ def _train_worker(rank, world, port, q, zero):
         dist.destroy_process_group()
 
 
+def _zero3_generate_worker(rank, world, port, q):
+    import torch.distributed as dist
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // (2 * world)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ops_emulation.install()
+        from cambrian_b200.sharded import Zero3Inference
+        cfg = tiny_cambrian_config()
+        model = _build(cfg).eval()                             # identical replicas
+        g = torch.Generator().manual_seed(40 + rank)           # every rank decodes its own sequence
+        L = 24 + 3 * rank                                      # different prompt lengths: ranks stay in lock-step anyway
+        ids = torch.randint(3, cfg.vocab_size, (1, L), generator=g)
+        ids[:, cfg.image_position] = -200
+        feats = _tower_feats(model, cfg, 1, 60 + rank)
+        type(model).encode_images = lambda self, imgs: feats
+        images = [torch.zeros(1, 3, 8, 8, dtype=torch.bfloat16) for _ in feats]
+        kw = dict(images=images, image_sizes=[(336, 336)], max_new_tokens=5)
+        ref = model.generate(ids, **kw)                        # unsharded
+        z = Zero3Inference(model)
+        shard_elems = sum(s_.numel() for s_ in z.shards)
+        got = model.generate(ids, **kw)                        # decoder layers sharded 1/world, gathered a layer ahead
+        ok = torch.equal(ref, got) and z.gathers >= 5 * cfg.num_hidden_layers
+        q.put((rank, bool(ok), f"ref {ref.tolist()} got {got.tolist()} gathers {z.gathers} shard elems {shard_elems}"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, False, traceback.format_exc()[-2500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_zero3_sharded_generate_two_ranks_gloo():
+    """BASELINE config 5's scheme on CPU: decoder layers sharded over two gloo ranks and all-gathered one layer ahead while
+    every rank runs `generate()` on its own sequence — token-identical to the unsharded model."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 37500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_zero3_generate_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+    assert all(r[1] for r in res), [r[2] for r in res]
+
+
 @pytest.mark.parametrize("zero", [0, 2])
 def test_whole_model_data_parallel_two_ranks_gloo(zero):
     """SURVEY §8e on CPU: the full tiny Cambrian model (connector + decoder with in-LLM SVA sites + fused loss) under
