@@ -203,7 +203,7 @@ def test_greedy_generate_host_logic(monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ N > 1 on gloo
-def _train_worker(rank, world, port, q, zero):
+def _train_worker(rank, world, port, q, zero, vary_labels=False):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // (2 * world)))   # two workers share the host: no oversubscription
@@ -228,10 +228,20 @@ def _train_worker(rank, world, port, q, zero):
         dist.all_reduce = counting
         eng = TrainEngine(model, lr=2e-3, bucket_mb=1.0, zero_stage=zero, max_grad_norm=1.0)
         losses = []
-        for _ in range(3):
+        from cambrian_b200.train.collator import valid_label_ranges
+        for step in range(3):
+            lab, hints = labels, {}
+            if vary_labels:
+                # the label layout differs per rank AND per step: the lm_head's chunk count and the rows it
+                # processes are data-dependent, the engine's collective schedule must not be
+                gl = torch.Generator().manual_seed(100 * step + rank)
+                lab = labels.clone()
+                lab[torch.rand(lab.shape, generator=gl) < 0.4] = -100
+                ranges, nv = valid_label_ranges(lab)
+                hints = dict(label_ranges=ranges, num_valid_labels=nv)
             eng.zero_grad()
-            loss = model(input_ids=ids, labels=labels, attention_mask=attn, position_ids=pos, images=images,
-                         image_aux_attention_masks_list=masks).loss
+            loss = model(input_ids=ids, labels=lab, attention_mask=attn, position_ids=pos, images=images,
+                         image_aux_attention_masks_list=masks, **hints).loss
             calls["bwd"] = True
             loss.backward()
             calls["bwd"] = False
@@ -244,7 +254,7 @@ def _train_worker(rank, world, port, q, zero):
         ok = bool(torch.equal(lo, hi))                                      # replicas bit-identical after 3 steps
         ok &= eng._overlap_ok and len(eng.buckets) >= 4
         ok &= calls["n"] >= len(eng.buckets)                               # collectives were issued from inside backward
-        ok &= losses[-1] < losses[0]                                        # and the job trains
+        ok &= vary_labels or losses[-1] < losses[0]                         # and the job trains
         if zero == 2:
             ok &= eng.master.numel() * world == eng.total
         q.put((rank, bool(ok), f"losses {losses} buckets {len(eng.buckets)} in-backward collectives {calls['n']} "
@@ -303,15 +313,16 @@ def test_zero3_sharded_generate_two_ranks_gloo():
     assert all(r[1] for r in res), [r[2] for r in res]
 
 
-@pytest.mark.parametrize("zero", [0, 2])
-def test_whole_model_data_parallel_two_ranks_gloo(zero):
+@pytest.mark.parametrize("zero,vary_labels", [(0, False), (2, False), (2, True)])
+def test_whole_model_data_parallel_two_ranks_gloo(zero, vary_labels):
     """SURVEY §8e on CPU: the full tiny Cambrian model (connector + decoder with in-LLM SVA sites + fused loss) under
-    TrainEngine on two gloo ranks — DDP all-reduce buckets and the ZeRO-2 sharded optimizer, gradient clipping on."""
+    TrainEngine on two gloo ranks — DDP all-reduce buckets and the ZeRO-2 sharded optimizer, gradient clipping on; one
+    variant with label layouts (and the collator's label-range hints) that differ per rank and per step."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 35500 + (os.getpid() + 29 * zero) % 2000
-    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, zero)) for r in range(2)]
+    port = 35500 + (os.getpid() + 29 * zero + 7 * int(vary_labels)) % 2000
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, zero, vary_labels)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=600) for _ in procs), key=lambda r: r[0])
