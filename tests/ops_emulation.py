@@ -473,6 +473,9 @@ class _Setter:
 def install(monkeypatch=None):
     """Replace the emulated entry points of `cambrian_b200.ops` for the duration of one test (pytest's monkeypatch undoes
     it; a spawned worker passes nothing); every other op keeps raising without the CUDA library."""
+    if torch.cuda.is_available():
+        raise RuntimeError("tests/ops_emulation.py: refusing to install kernel stand-ins in a process that can see a GPU — "
+                           "they exist for host-logic tests on GPU-less machines, not as a fallback")
     monkeypatch = monkeypatch or _Setter
     from cambrian_b200 import ops
     for n in _NAMES:
